@@ -1,0 +1,126 @@
+/*
+ * polar_b200 -- C ABI of the B200 (sm_100a) LLR-domain SC / SCL polar decoder.
+ *
+ * This is the drop-in boundary for the reference's hot path. The reference
+ * (tavildar/Polar, PolarC/) has no FFI layer of its own: its boundary is the
+ * C++ class surface PolarC/PolarCode.h:19-34. The host class shipped with this
+ * library (polar_b200/csrc/PolarCode.h, same public signatures) is implemented on
+ * top of the entry points below, and every entry point names the reference
+ * interface it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this ABI;
+ *   - return value 0 = OK, negative = POLAR_B200_E_* (invalid use), positive =
+ *     a cudaError_t passed through; polar_b200_strerror() explains both;
+ *   - no exceptions cross the ABI;
+ *   - a ctx is bound to one device; calls on one ctx must be serialised by the
+ *     caller (like the reference object, PolarCode.h:56-68, it is not
+ *     re-entrant); different ctxs are independent;
+ *   - "device" pointers are CUDA device pointers on the ctx's device; the
+ *     *_host entry points take ordinary (ideally pinned) host memory and do the
+ *     transfers themselves;
+ *   - LLR sign convention is the reference's: LLR = ln P(y|0)/P(y|1), positive
+ *     means bit 0 (PolarCode.cpp:752 with BPSK 0 -> -1 at :715);
+ *   - decoded info bits are packed little-endian: bit j of codeword b is
+ *     (info_packed[b * polar_b200_info_words(K) + j/32] >> (j%32)) & 1, where j is
+ *     the reference's info index (decoded[j] of PolarCode.cpp:171-174).
+ */
+#ifndef POLAR_B200_H
+#define POLAR_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct polar_b200_ctx polar_b200_ctx;
+
+enum {
+    POLAR_B200_OK = 0,
+    POLAR_B200_E_ARG = -1,        /* null pointer / out-of-range argument            */
+    POLAR_B200_E_UNSUPPORTED = -2,/* valid for the reference, not for this build     */
+    POLAR_B200_E_NOGPU = -3,      /* no usable CUDA device: there is NO CPU fallback */
+    POLAR_B200_E_BATCH = -4,      /* B exceeds the ctx's max_batch                   */
+    POLAR_B200_E_LIST = -5        /* list size < 1, > max_list or > 32               */
+};
+
+/* ABI version of this header; polar_b200_abi_version() must return the same value. */
+#define POLAR_B200_ABI_VERSION 1
+int polar_b200_abi_version(void);
+
+/* Human-readable text for any value returned by this library. */
+const char* polar_b200_strerror(int code);
+
+/* Words of packed output per codeword: ceil(K/32). */
+int polar_b200_info_words(int K);
+
+/*
+ * Create a decoder for one polar code on one device.
+ *
+ * Replaces the per-object state the reference builds in its constructor
+ * (PolarCode.h:19-28 -> PolarCode.cpp:17-58, 647-656). The construction itself
+ * (Bhattacharyya recursion, std::sort, rand() parity matrix) stays on the host
+ * C++ side and is passed in as data, so this library is independent of
+ * rand()/std::sort quirks:
+ *   n            log2 of the block length N, 1 <= n <= 12
+ *   K            info bits; crc_bits parity ("CRC") bits, K + crc_bits <= N
+ *   frozen_mask  [N] bytes, 1 = frozen, index = decoding position phi (_frozen_bits)
+ *   info_order   [K + crc_bits] = prefix of _channel_order_descending: position of info
+ *                bit j (j < K) and of parity bit r (at K + r)
+ *   crc_matrix   [crc_bits][K] row-major 0/1 (_crc_matrix); may be NULL when crc_bits == 0
+ *   max_list     largest list size that will be requested (1..32)
+ *   max_batch    largest B for the *_host entry points (sizes the staging buffers;
+ *                the device-pointer entry points accept any B)
+ */
+int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bits,
+                      const uint8_t* frozen_mask, const uint16_t* info_order,
+                      const uint8_t* crc_matrix, int max_list, int max_batch);
+
+int polar_b200_destroy(polar_b200_ctx* ctx);
+
+/*
+ * Decode B codewords. Replaces B calls of
+ *   std::vector<uint8_t> PolarCode::decode_scl_llr(std::vector<double> llr, uint16_t list_size)
+ * (PolarCode.h:32, PolarCode.cpp:130-190, 422-644).
+ *   llr          device, [B][N] row-major fp32, the reference's channel order
+ *   L            list size, 1 <= L <= max_list (L = 1 is plain SC); need not be a power of two
+ *   info_packed  device, [B][polar_b200_info_words(K)]
+ *   cuda_stream  a cudaStream_t (NULL = default stream); the call is asynchronous on it
+ */
+int polar_b200_decode_scl_llr(polar_b200_ctx* ctx, const float* llr, int B, int L,
+                              uint32_t* info_packed, void* cuda_stream);
+
+/*
+ * Same, host memory in and out: H2D copy of llr, decode, D2H copy of the packed bits,
+ * then a stream synchronise (the result is valid on return). This is the end-to-end
+ * path the host class and bench.py's `e2e` leg use. B <= max_batch.
+ */
+int polar_b200_decode_scl_llr_host(polar_b200_ctx* ctx, const float* llr_host, int B, int L,
+                                   uint32_t* info_packed_host, void* cuda_stream);
+
+/*
+ * Block-error flags: block_err[b] = 1 iff any of the K info bits differ. Replaces the
+ * comparison loop of the BLER harness (PolarCode.cpp:758-764). All device pointers;
+ * n_err (device, may be NULL) is incremented by the number of block errors.
+ */
+int polar_b200_count_errors(polar_b200_ctx* ctx, const uint32_t* info_packed,
+                            const uint32_t* truth_packed, int B, uint8_t* block_err,
+                            unsigned long long* n_err, void* cuda_stream);
+
+/* Introspection (all return -1 for an unknown key). */
+enum {
+    POLAR_B200_INFO_KERNEL_LAUNCHES = 0, /* kernels this ctx has launched so far            */
+    POLAR_B200_INFO_SM_COUNT = 1,
+    POLAR_B200_INFO_WARPS_PER_BLOCK = 2, /* of the last decode launch                       */
+    POLAR_B200_INFO_BLOCKS = 3,          /* grid size of the last decode launch             */
+    POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
+    POLAR_B200_INFO_SCRATCH_BYTES = 5    /* device scratch owned by the ctx                 */
+};
+long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* POLAR_B200_H */

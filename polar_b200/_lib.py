@@ -1,0 +1,77 @@
+"""ctypes loader for the native libraries. Fails loudly: there is no Python or CPU fallback."""
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(PKG, "lib")
+DEV_SO = os.path.join(LIB_DIR, "libpolar_b200.so")
+HOST_SO = os.path.join(LIB_DIR, "libpolar_host.so")
+
+_dev = None
+_host = None
+
+
+class PolarB200Error(RuntimeError):
+    pass
+
+
+def _need(path):
+    if not os.path.exists(path):
+        raise PolarB200Error(
+            "%s is missing: build it with `python -m polar_b200.build` (needs nvcc). "
+            "polar_b200 has no CPU fallback." % path)
+    return path
+
+
+def dev():
+    """libpolar_b200.so with argtypes set for every symbol of include/polar_b200.h."""
+    global _dev
+    if _dev is None:
+        lib = C.CDLL(_need(DEV_SO), mode=C.RTLD_GLOBAL)
+        vp, ip = C.c_void_p, C.c_int
+        lib.polar_b200_abi_version.restype = ip
+        lib.polar_b200_strerror.restype = C.c_char_p
+        lib.polar_b200_strerror.argtypes = [ip]
+        lib.polar_b200_info_words.argtypes = [ip]
+        lib.polar_b200_create.argtypes = [C.POINTER(vp), ip, ip, ip, ip, vp, vp, vp, ip, ip]
+        lib.polar_b200_destroy.argtypes = [vp]
+        lib.polar_b200_decode_scl_llr.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_decode_scl_llr_host.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_count_errors.argtypes = [vp, vp, vp, ip, vp, vp, vp]
+        lib.polar_b200_get_info.restype = C.c_longlong
+        lib.polar_b200_get_info.argtypes = [vp, ip]
+        _dev = lib
+    return _dev
+
+
+def host():
+    """libpolar_host.so (the C++ PolarCode class behind C wrappers)."""
+    global _host
+    if _host is None:
+        dev()
+        lib = C.CDLL(_need(HOST_SO))
+        vp, ip = C.c_void_p, C.c_int
+        lib.polar_host_last_error.restype = C.c_char_p
+        lib.polar_host_create.restype = vp
+        lib.polar_host_create.argtypes = [ip, ip, C.c_double, ip, ip, ip]
+        lib.polar_host_destroy.argtypes = [vp]
+        lib.polar_host_get_construction.argtypes = [vp, vp, vp, vp, vp]
+        lib.polar_host_encode.argtypes = [vp, vp, ip, vp]
+        lib.polar_host_decode_scl_llr.argtypes = [vp, vp, ip, vp]
+        lib.polar_host_decode_batch_packed.argtypes = [vp, vp, ip, ip, vp]
+        lib.polar_host_decode_device.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_host_ctx.restype = vp
+        lib.polar_host_ctx.argtypes = [vp, ip]
+        lib.polar_host_get_bler_quick.argtypes = [vp, vp, ip, vp, ip, ip, ip, ip, vp]
+        _host = lib
+    return _host
+
+
+def check(rc, what="polar_b200"):
+    if rc != 0:
+        raise PolarB200Error("%s: %s" % (what, dev().polar_b200_strerror(rc).decode()))
+
+
+def check_host(rc, what="polar_host"):
+    if rc != 0:
+        raise PolarB200Error("%s: %s" % (what, host().polar_host_last_error().decode()))

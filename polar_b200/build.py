@@ -1,0 +1,85 @@
+"""In-tree build of the native libraries (nvcc cross-compiles sm_100a without a GPU).
+
+    polar_b200/lib/libpolar_b200.so   CUDA kernels + the C ABI of include/polar_b200.h
+    polar_b200/lib/libpolar_host.so   the C++ drop-in `PolarCode` class + ctypes wrappers
+
+`python -m polar_b200.build` rebuilds what is stale; `--force` rebuilds everything.
+The .so files are git-ignored but travel to the GPU box with the tree.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+CSRC = os.path.join(PKG, "csrc")
+LIB = os.path.join(PKG, "lib")
+INC = os.path.join(ROOT, "include")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC,
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: the CUDA library cannot be built (there is no CPU fallback)")
+
+
+def _stale(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(LIB, exist_ok=True)
+    hdrs = [os.path.join(INC, "polar_b200.h"), os.path.join(CSRC, "PolarCode.h")]
+    dev_so = os.path.join(LIB, "libpolar_b200.so")
+    dev_src = [os.path.join(CSRC, "polar_b200.cu")]
+    if force or _stale(dev_so, dev_src + hdrs):
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + dev_src + ["-o", dev_so]
+        subprocess.check_call(cmd)
+    host_so = os.path.join(LIB, "libpolar_host.so")
+    host_src = [os.path.join(CSRC, "PolarCode.cpp")]
+    if force or _stale(host_so, host_src + hdrs + [dev_so]):
+        cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC] + host_src + [
+            "-L" + LIB, "-lpolar_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-o", host_so]
+        subprocess.check_call(cmd)
+    return dev_so, host_so
+
+
+def build_acceptance(ref_dir="/root/reference/PolarC"):
+    """The reference's UNMODIFIED main.cpp compiled against this repo's PolarCode.h (the drop-in
+    test of SURVEY.md section 4 item 3). Output goes next to the compiled reference in oracle/_ref/
+    (git-ignored; the source is compiled where it lies, never copied)."""
+    main_cpp = os.path.join(ref_dir, "main.cpp")
+    if not os.path.exists(main_cpp):
+        return None
+    out_dir = os.path.join(ROOT, "oracle", "_ref")
+    os.makedirs(out_dir, exist_ok=True)
+    exe = os.path.join(out_dir, "polar_b200_main")
+    srcs = [main_cpp, os.path.join(CSRC, "PolarCode.h"), os.path.join(LIB, "libpolar_host.so")]
+    if _stale(exe, srcs):
+        # -I CSRC first so that `#include "PolarCode.h"` resolves to the drop-in header; nvcc's
+        # host compiler looks in the including file's own directory first for quoted includes, so
+        # the file is fed through stdin-less indirection: compile a one-line TU that includes it.
+        shim = os.path.join(out_dir, "main_shim.cpp")
+        with open(shim, "w") as f:
+            f.write('#include "PolarCode.h"\n#define POLARC_POLARCODE_H\n#include "%s"\n' % main_cpp)
+        rpath = os.path.relpath(LIB, out_dir)
+        cmd = ["g++", "-std=c++11", "-O2", "-I" + CSRC, shim, "-L" + LIB, "-lpolar_host", "-lpolar_b200",
+               "-Wl,-rpath,$ORIGIN/" + rpath, "-o", exe]
+        subprocess.check_call(cmd)
+    return exe
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    build_acceptance()
+    print("built:", os.listdir(LIB))

@@ -1,0 +1,151 @@
+"""Python mirror of the drop-in `PolarCode` class (polar_b200/csrc/PolarCode.h), which itself
+mirrors the reference's PolarC/PolarCode.h:19-34: constructor(n, K, epsilon, crc), encode,
+decode_scl_llr, get_bler_quick -- plus the batched entry points.
+
+Everything here is a thin ctypes veneer: construction, encoding and the BLER harness run in the
+C++ host class, decoding runs in the CUDA library. Nothing falls back to Python or CPU decoding.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def _ptr(x):
+    """raw address of a numpy array or torch tensor"""
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+def unpack_bits(packed, K):
+    """[B][KW] uint32 (numpy) -> [B][K] uint8"""
+    packed = np.ascontiguousarray(packed, np.uint32)
+    bits = np.unpackbits(packed.view(np.uint8), axis=-1, bitorder="little")
+    return np.ascontiguousarray(bits[..., :K])
+
+
+def pack_bits(bits):
+    """[B][K] 0/1 -> [B][ceil(K/32)] uint32, bit j of a row at word j//32, bit j%32"""
+    bits = np.ascontiguousarray(bits, np.uint8)
+    B, K = bits.shape
+    KW = (K + 31) // 32
+    pad = np.zeros((B, KW * 32), np.uint8)
+    pad[:, :K] = bits
+    return np.packbits(pad, axis=-1, bitorder="little").view(np.uint32).reshape(B, KW)
+
+
+class PolarCode:
+    def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True, device=0):
+        """n = log2(block length) as in the C++ reference (PolarCode.h:19). reseed=True calls
+        srand(1) first so the random parity matrix (PolarCode.cpp:51-56) is the one a fresh
+        reference process draws."""
+        self._h = None
+        lib = _lib.host()
+        self.n, self.N, self.K, self.crc = int(n), 1 << int(n), int(K), int(crc)
+        self.KW = (self.K + 31) // 32
+        self.device = int(device)
+        self._h = lib.polar_host_create(self.n, self.K, float(epsilon), self.crc, 1 if reseed else 0, self.device)
+        if not self._h:
+            raise _lib.PolarB200Error("PolarCode: " + lib.polar_host_last_error().decode())
+
+    def close(self):
+        if self._h:
+            _lib.host().polar_host_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- construction tables (PolarCode.h:43-46) ----
+    def construction(self):
+        frozen = np.zeros(self.N, np.uint8)
+        order = np.zeros(self.N, np.uint16)
+        bitrev = np.zeros(self.N, np.uint16)
+        crcm = np.zeros((max(self.crc, 1), self.K), np.uint8)
+        _lib.host().polar_host_get_construction(self._h, frozen.ctypes.data, order.ctypes.data, crcm.ctypes.data,
+                                                bitrev.ctypes.data)
+        return dict(frozen=frozen, order=order, crc_matrix=crcm[: self.crc], bitrev=bitrev)
+
+    # ---- PolarCode.h:30 ----
+    def encode(self, info):
+        info = np.ascontiguousarray(info, np.uint8)
+        single = info.ndim == 1
+        info2 = info.reshape(-1, self.K)
+        out = np.zeros((info2.shape[0], self.N), np.uint8)
+        _lib.check_host(_lib.host().polar_host_encode(self._h, info2.ctypes.data, info2.shape[0], out.ctypes.data))
+        return out[0] if single else out
+
+    # ---- PolarCode.h:32: one codeword, double LLRs in, K bytes out ----
+    def decode_scl_llr(self, llr, list_size):
+        llr = np.ascontiguousarray(llr, np.float64)
+        if llr.shape != (self.N,):
+            raise ValueError("llr must have shape (N,)")
+        out = np.zeros(self.K, np.uint8)
+        _lib.check_host(_lib.host().polar_host_decode_scl_llr(self._h, llr.ctypes.data, int(list_size), out.ctypes.data))
+        return out
+
+    # ---- batched, host memory (numpy or pinned torch CPU tensors) ----
+    def decode_batch(self, llr, list_size, packed=False, out=None):
+        """llr: [B][N] float32 in host memory. Returns [B][K] uint8 bits, or the packed
+        [B][KW] uint32 words if packed=True. H2D, decode and D2H all happen inside the call."""
+        if isinstance(llr, np.ndarray):
+            llr = np.ascontiguousarray(llr, np.float32).reshape(-1, self.N)
+        B = int(llr.shape[0])
+        if out is None:
+            out = np.zeros((B, self.KW), np.uint32)
+        _lib.check_host(_lib.host().polar_host_decode_batch_packed(self._h, _ptr(llr), B, int(list_size), _ptr(out)))
+        if packed or not isinstance(out, np.ndarray):
+            return out
+        return unpack_bits(out, self.K)
+
+    # ---- batched, device memory (torch CUDA tensors), asynchronous on the current stream ----
+    def decode_device(self, llr, list_size, out=None, stream=None):
+        import torch
+        assert llr.is_cuda and llr.dtype == torch.float32 and llr.is_contiguous()
+        B = llr.numel() // self.N
+        if out is None:
+            out = torch.empty((B, self.KW), dtype=torch.int32, device=llr.device)
+        if stream is None:
+            stream = torch.cuda.current_stream(llr.device).cuda_stream
+        _lib.check_host(_lib.host().polar_host_decode_device(self._h, llr.data_ptr(), B, int(list_size), out.data_ptr(),
+                                                             C.c_void_p(stream)))
+        return out
+
+    def count_errors(self, dec, truth, block_err=None, n_err=None, stream=None):
+        """device tensors [B][KW] int32; fills block_err (uint8 [B]) / adds to n_err (int64 [1])."""
+        import torch
+        B = dec.shape[0]
+        if stream is None:
+            stream = torch.cuda.current_stream(dec.device).cuda_stream
+        ctx = self.ctx(1)
+        _lib.check(_lib.dev().polar_b200_count_errors(
+            ctx, dec.data_ptr(), truth.data_ptr(), B, block_err.data_ptr() if block_err is not None else None,
+            n_err.data_ptr() if n_err is not None else None, C.c_void_p(stream)))
+
+    def ctx(self, min_batch=1):
+        c = _lib.host().polar_host_ctx(self._h, int(min_batch))
+        if not c:
+            raise _lib.PolarB200Error("PolarCode.ctx: " + _lib.host().polar_host_last_error().decode())
+        return c
+
+    def info(self, key):
+        return int(_lib.dev().polar_b200_get_info(self.ctx(1), int(key)))
+
+    @property
+    def kernel_launches(self):
+        return self.info(0)
+
+    # ---- PolarCode.h:34 ----
+    def get_bler_quick(self, ebno_vec, list_sizes, max_err=100, max_runs=1000, verbose=False):
+        ebno = np.ascontiguousarray(ebno_vec, np.float64)
+        lists = np.ascontiguousarray(list_sizes, np.uint8)
+        bler = np.zeros((len(lists), len(ebno)), np.float64)
+        _lib.check_host(_lib.host().polar_host_get_bler_quick(self._h, ebno.ctypes.data, len(ebno), lists.ctypes.data,
+                                                              len(lists), int(max_err), int(max_runs), 1 if verbose else 0,
+                                                              bler.ctypes.data))
+        return bler

@@ -1,0 +1,87 @@
+// Host-side drop-in for the reference's `class PolarCode` (PolarC/PolarCode.h:16-90).
+//
+// Same public surface -- constructor (num_layers, info_length, epsilon, crc_size), encode,
+// decode_scl_p1, decode_scl_llr, get_bler_quick -- so that the reference's own driver
+// (PolarC/main.cpp:15,32) compiles against this header unchanged. The LLR-domain decoder,
+// the only thing the reference's BLER loop calls (PolarCode.cpp:756), runs on the GPU
+// through the C ABI of include/polar_b200.h; there is no CPU decoder behind it and every
+// decode throws std::runtime_error if the CUDA library cannot be used.
+//
+// Additions over the reference surface are the batched entry points a throughput user
+// needs (decode_scl_llr_batch*, accessors for the construction tables).
+#ifndef POLAR_B200_POLARCODE_H
+#define POLAR_B200_POLARCODE_H
+
+#include <cstdint>
+#include <vector>
+
+struct polar_b200_ctx;
+
+class PolarCode {
+public:
+    // PolarCode.h:19-28. num_layers = log2(block length) as in the C++ reference (the MATLAB twin
+    // takes N). Side effect kept: consumes crc_size * info_length values of rand() for the
+    // random parity ("CRC") matrix, PolarCode.cpp:51-56.
+    PolarCode(uint8_t num_layers, uint16_t info_length, double epsilon, uint16_t crc_size);
+    ~PolarCode();
+    PolarCode(const PolarCode&) = delete;
+    PolarCode& operator=(const PolarCode&) = delete;
+
+    // PolarCode.h:30 / PolarCode.cpp:60-91. Host code (negligible next to decoding).
+    std::vector<uint8_t> encode(std::vector<uint8_t> info_bits);
+    // PolarCode.h:31. Probability-domain list decoding is outside the accelerated path
+    // (the reference's harness never calls it, PolarCode.cpp:755 is commented out): throws.
+    std::vector<uint8_t> decode_scl_p1(std::vector<double> p1, std::vector<double> p0, uint16_t list_size);
+    // PolarCode.h:32 / PolarCode.cpp:130-190. One codeword, GPU, latency-bound; kept for source
+    // compatibility. LLRs are rounded to float before decoding.
+    std::vector<uint8_t> decode_scl_llr(std::vector<double> llr, uint16_t list_size);
+    // PolarCode.h:34 / PolarCode.cpp:658-785. Same RNG objects in the same call order, same
+    // counting rules (early stop, decoded-at-lower-Eb/N0 shortcut) replayed on the host over
+    // per-cell success flags; all decodes of a sweep are batched on the GPU.
+    std::vector<std::vector<double>> get_bler_quick(std::vector<double> ebno_vec, std::vector<uint8_t> list_size);
+
+    // ---- batched extensions ----
+    // llr: host, [B][N] floats. Returns [B][K] bytes (0/1).
+    std::vector<uint8_t> decode_scl_llr_batch(const float* llr, int B, uint16_t list_size);
+    // Same with packed output: [B][info_words()] little-endian words.
+    void decode_scl_llr_batch_packed(const float* llr, int B, uint16_t list_size, uint32_t* info_packed);
+    // Device pointers, asynchronous on `cuda_stream` (a cudaStream_t).
+    void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream);
+
+    int block_length() const { return _block_length; }
+    int info_length() const { return _info_length; }
+    int crc_size() const { return _crc_size; }
+    int num_layers() const { return _n; }
+    int info_words() const { return (_info_length + 31) / 32; }
+    const std::vector<uint8_t>& frozen_bits() const { return _frozen_bits; }
+    const std::vector<uint16_t>& channel_order() const { return _channel_order_descending; }
+    const std::vector<std::vector<uint8_t>>& crc_matrix() const { return _crc_matrix; }
+    const std::vector<uint16_t>& bit_rev_order() const { return _bit_rev_order; }
+    polar_b200_ctx* device_ctx(int min_batch);   // creates / grows the GPU context on demand
+
+    // knobs of get_bler_quick, defaults = the reference's constants (PolarCode.cpp:661-662)
+    int bler_max_err = 100;
+    int bler_max_runs = 1000;
+    bool bler_verbose = true;      // the reference's "Running iteration ..." lines
+    int device = 0;                // CUDA device ordinal
+
+private:
+    uint8_t _n;
+    uint16_t _info_length;
+    uint16_t _block_length;
+    uint16_t _crc_size;
+    double _design_epsilon;
+
+    std::vector<uint8_t> _frozen_bits;
+    std::vector<uint16_t> _channel_order_descending;
+    std::vector<std::vector<uint8_t>> _crc_matrix;
+    std::vector<uint16_t> _bit_rev_order;
+
+    polar_b200_ctx* _ctx = nullptr;
+    int _ctx_batch = 0;
+
+    void initialize_frozen_bits();
+    void create_bit_rev_order();
+};
+
+#endif  // POLAR_B200_POLARCODE_H

@@ -1,0 +1,674 @@
+// polar_b200 -- LLR-domain SC / SCL polar decoder for B200 (sm_100a); C ABI in include/polar_b200.h.
+//
+// What is computed is the reference's decode_scl_llr (PolarC/PolarCode.cpp:130-190,
+// 422-644): Tal-Vardy successive-cancellation list decoding with LLR path metrics,
+// the reference's own check-node rule (exact box-plus below |LLR| = 40, sign-min
+// above, PolarCode.cpp:438-446) and its literal softplus metric updates
+// (PolarCode.cpp:483,505-506). How it is computed is not the reference's:
+//
+//   * one WARP owns a group of 32/W codewords (W = list size rounded up to a power of
+//     two); lane = one list path of one codeword, so the 2L-way fork / prune is a
+//     handful of warp shuffles and ballots and there is no block-level barrier at all;
+//   * every layer array is stored "path-interleaved" ([beta][lane], one 128-byte row per
+//     tree node position): a lane's own column is written, any column can be read, and
+//     both are bank-conflict-free in shared memory and fully coalesced in HBM/L2;
+//   * the reference's lazy copy (ref-counted array pools, PolarCode.cpp:195-373) becomes a
+//     5-bit column pointer per (path, layer), packed in two 64-bit registers; cloning a
+//     path is a register shuffle. All paths recompute a given layer at the same time and
+//     always write their own column, so a pointer can never dangle;
+//   * arrays are kept in "butterfly" order (pairs (beta, beta+M) instead of the
+//     reference's (2beta, 2beta+1)); the bit-reversal this implies is folded into the
+//     first layer's channel reads. Partial sums are bit-packed, and combining the two
+//     halves of a node is a word concatenation;
+//   * decided bits are not stored per path: the last partial-sum update yields the
+//     re-encoded codeword of every path, and one packed polar transform turns it back
+//     into u-hat for the parity ("CRC") check and the output gather;
+//   * the small layers live in shared memory, the big ones (touched rarely) in a
+//     per-warp scratch in HBM that stays L2-resident.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "polar_b200.h"
+
+#define FULL_MASK 0xffffffffu
+
+namespace {
+
+constexpr int kMaxN = 13;          // log2 block length supported by the pointer packing (12 x 5 bits)
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct DecodeArgs {
+    const float* llr;            // [B][N]
+    uint32_t* out;               // [B][KW]
+    const uint32_t* frozen_words;// [max(1,N/32)], bit phi set = frozen
+    const uint16_t* info_order;  // [K + crc]
+    const uint32_t* crc_masks;   // [crc][NW] over phi
+    float* gx;                   // per-warp LLR scratch rows (32 floats each)
+    uint32_t* gs;                // per-warp partial-sum scratch rows (32 words each)
+    unsigned long long gx_stride;// floats per warp
+    unsigned long long gs_stride;// words per warp
+    int B, n, K, crc, L;
+    int W;                       // lanes per codeword (power of two >= L)
+    int lamS;                    // first LLR layer kept in shared memory (1..n)
+    int smem_x_rows;             // rows of 32 floats per warp
+    int smem_s_rows;             // rows of 32 words per warp
+    int s_off[kMaxN + 2];        // word-row offset of S layer lam (global for lam < lamS, shared otherwise)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_approx(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// log(1 + exp(-x)) for x >= 0, in (0, ln 2].
+__device__ __forceinline__ float log1p_exp_neg(float x) {
+    return kLn2 * lg2_approx(1.0f + ex2_approx(-kLog2e * x));
+}
+
+// The reference's check-node rule (PolarCode.cpp:438-446): box-plus when both magnitudes
+// are strictly below 40, sign * min otherwise (sgn(0) = 0, which min() already yields).
+// Box-plus is evaluated as sign*min + log1p(e^-|a+b|) - log1p(e^-|a-b|): algebraically the
+// reference's log((e^(a+b)+1)/(e^a+e^b)), but with an absolute error of a few 1e-7 at every
+// magnitude (the literal form loses that much *relative* to e^40 in fp32).
+__device__ __forceinline__ float f_rule(float a, float b) {
+    const float ma = fabsf(a), mb = fabsf(b);
+    const float mn = fminf(ma, mb);
+    float r = __int_as_float(__float_as_int(mn) | ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
+    if (fmaxf(ma, mb) < 40.0f) {
+        const float s = fabsf(a + b), d = fabsf(a - b);
+        r += kLn2 * (lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d)));
+    }
+    return r;
+}
+
+// log(1 + exp(x)) with the double-precision reference's corner behaviour
+// (PolarCode.cpp:483,505-506): +inf once exp(x) overflows a double (x > 709.78...),
+// exactly 0 once 1 + exp(x) rounds to 1 in double (x < -36.7368...).
+__device__ __forceinline__ float softplus_ref(float x) {
+    float r = fmaxf(x, 0.0f) + log1p_exp_neg(fabsf(x));
+    if (x >= 709.78271484375f) r = CUDART_INF_F;
+    if (x <= -36.7368f) r = 0.0f;
+    return r;
+}
+
+__device__ __forceinline__ float group_min(float v, int W) {
+    for (int o = W >> 1; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ float group_max(float v, int W) {
+    for (int o = W >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+
+__device__ __forceinline__ unsigned long long set_ptr(unsigned long long p, int idx, unsigned lane) {
+    const int sh = 5 * idx;
+    return (p & ~(31ull << sh)) | ((unsigned long long)lane << sh);
+}
+__device__ __forceinline__ int get_ptr(unsigned long long p, int idx) { return (int)((p >> (5 * idx)) & 31ull); }
+
+// One warp decodes groups of 32/W codewords. Dynamic shared memory per warp:
+//   smem_x_rows rows of 32 floats (LLR layers lamS..n-1), smem_s_rows rows of 32 words
+//   (partial-sum layers >= max(lamS,1), except layer n which is a register), 32 bytes of scatter
+//   scratch.
+__global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int gwarp = blockIdx.x * warps_per_block + warp_in_block;
+    const int total_warps = gridDim.x * warps_per_block;
+
+    const int n = a.n, N = 1 << n, L = a.L, W = a.W, lamS = a.lamS;
+    const int G = 32 / W;                      // codewords per warp
+    const int slot = lane & (W - 1);           // path index within the codeword
+    const int gbase = lane & ~(W - 1);         // first lane of my codeword
+    const unsigned gmask_lo = (W == 32) ? FULL_MASK : ((1u << W) - 1u);
+    const int NW = (N + 31) >> 5;              // words in an N-bit vector
+    const int KW = (a.K + 31) >> 5;
+
+    const size_t per_warp_smem = (size_t)(a.smem_x_rows + a.smem_s_rows) * 128 + 32;
+    unsigned char* my_smem = smem_raw + per_warp_smem * warp_in_block;
+    float* sx = reinterpret_cast<float*>(my_smem);
+    uint32_t* ss = reinterpret_cast<uint32_t*>(my_smem + (size_t)a.smem_x_rows * 128);
+    unsigned char* srcof = my_smem + (size_t)(a.smem_x_rows + a.smem_s_rows) * 128;
+    float* gx = a.gx + a.gx_stride * gwarp;
+    uint32_t* gs = a.gs + a.gs_stride * gwarp;
+
+    // Row address of LLR layer lam (1 <= lam <= n-1), position beta.
+    auto xrow = [&](int lam, int beta) -> float* {
+        if (lam >= lamS) return sx + ((size_t)((1 << (n - lamS + 1)) - (1 << (n - lam + 1)) + beta) << 5);
+        return gx + ((size_t)(N - (1 << (n - lam + 1)) + beta) << 5);
+    };
+    // Row address of partial-sum layer lam (0 <= lam <= n-1), word w.
+    const int lamSS = lamS < 1 ? 1 : lamS;
+    auto srow = [&](int lam, int w) -> uint32_t* {
+        if (lam >= lamSS) return ss + ((size_t)(a.s_off[lam] + w) << 5);
+        return gs + ((size_t)(a.s_off[lam] + w) << 5);
+    };
+
+    for (int grp = gwarp; grp * G < a.B; grp += total_warps) {
+        const int cw = grp * G + (lane / W);
+        const bool valid = cw < a.B;
+        const float* chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
+
+        // Per-path state. Reference bookkeeping reproduced: the free-path stack is filled
+        // 0..L-1 (PolarCode.cpp:250-256) and the first path popped is L-1 (:259-263).
+        bool active = valid && (slot == L - 1);
+        float pm = 0.0f;
+        unsigned long long px = 0, ps = 0;      // column pointers, 5 bits per layer (index lam-1)
+        uint32_t s_n = 0;                       // partial sum of layer n (the last even leaf's bit)
+        int stk = slot;                         // lane gbase+j holds free-path stack entry j
+        int sp = L - 1;                         // stack height (uniform within a codeword)
+        float lam_n = 0.0f;                     // LLR of layer n (decision LLR)
+        uint32_t frozen_word = 0;
+
+        for (int phi = 0; phi < N; ++phi) {
+            // ---- refresh LLR layers lam_top..n (PolarCode.cpp:422-455) ----
+            const int lam_top = (phi == 0) ? 1 : n - (__ffs(phi) - 1);
+            for (int lam = lam_top; lam <= n; ++lam) {
+                const int M = 1 << (n - lam);
+                const bool is_g = (lam == lam_top) && (phi != 0);
+                const float* src = nullptr;
+                if (lam > 1) src = xrow(lam - 1, 0) + get_ptr(px, lam - 2);
+                const uint32_t* sw = nullptr;
+                if (is_g && lam < n) sw = srow(lam, 0) + get_ptr(ps, lam - 1);
+                float* dst = (lam < n) ? xrow(lam, 0) + lane : nullptr;
+                if (active) {
+                    for (int i = 0; i < M; ++i) {
+                        float x0, x1;
+                        int beta = i;
+                        if (lam == 1) {
+                            // channel layer: reference pairs are (2k, 2k+1); k runs in memory
+                            // order, the result lands at the bit-reversed position.
+                            const float2 v = *reinterpret_cast<const float2*>(chan + 2 * i);
+                            x0 = v.x; x1 = v.y;
+                            beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
+                        } else {
+                            x0 = src[(size_t)i << 5];
+                            x1 = src[(size_t)(i + M) << 5];
+                        }
+                        float y;
+                        if (is_g) {
+                            uint32_t bit;
+                            if (lam == n) bit = s_n & 1u;
+                            else bit = (sw[(size_t)(beta >> 5) << 5] >> (beta & 31)) & 1u;
+                            y = x1 + (bit ? -x0 : x0);                      // PolarCode.cpp:448-451
+                        } else {
+                            y = f_rule(x0, x1);                              // PolarCode.cpp:438-446
+                        }
+                        if (lam == n) lam_n = y; else dst[(size_t)beta << 5] = y;
+                    }
+                }
+                if (lam < n) px = set_ptr(px, lam - 1, lane);
+            }
+
+            // ---- leaf decision ----
+            if ((phi & 31) == 0) frozen_word = a.frozen_words[phi >> 5];
+            const bool frozen = (frozen_word >> (phi & 31)) & 1u;
+            uint32_t u = 0;
+            if (frozen) {
+                // PolarCode.cpp:475-487
+                if (active) pm += softplus_ref(-lam_n);
+            } else {
+                // PolarCode.cpp:489-607. Metrics are kept positive (m = -probForks).
+                const float m0 = pm + softplus_ref(-lam_n);
+                const float m1 = pm + softplus_ref(lam_n);
+                const unsigned act_all = __ballot_sync(FULL_MASK, active);
+                const unsigned act_g = (act_all >> gbase) & gmask_lo;
+                const int A = __popc(act_g);
+                bool keep0 = active, keep1 = active;
+                const bool need_select = active && (2 * A > L);
+                bool slow = false;
+                if (need_select) {
+                    slow = true;
+                }
+                if (__any_sync(FULL_MASK, need_select)) {
+                    // fast exit: every likely fork strictly beats every unlikely fork, list is full
+                    const float lo = fminf(m0, m1), hi = fmaxf(m0, m1);
+                    const float worst_likely = group_max(active ? lo : -CUDART_INF_F, W);
+                    const float best_unlikely = group_min(active ? hi : CUDART_INF_F, W);
+                    if (need_select && A == L && best_unlikely > worst_likely) {
+                        slow = false;
+                        keep0 = (m0 <= m1);      // m0 == m1 cannot happen here (would not be strict)
+                        keep1 = !keep0;
+                    }
+                    if (__any_sync(FULL_MASK, slow)) {
+                        // exact rule: keep the rho best of the 2A forks under (metric asc, fork index asc)
+                        // == PolarCode.cpp:528-553 (sort, threshold, '>' pass then '==' pass in index order).
+                        int r0 = 0, r1 = 0;
+                        for (int j = 0; j < W; ++j) {
+                            const float o0 = __shfl_sync(FULL_MASK, m0, gbase + j);
+                            const float o1 = __shfl_sync(FULL_MASK, m1, gbase + j);
+                            const bool oa = (act_g >> j) & 1u;
+                            if (oa) {
+                                // other fork indices 2j, 2j+1; mine 2*slot, 2*slot+1
+                                r0 += (o0 < m0) || (o0 == m0 && j < slot);
+                                r0 += (o1 < m0) || (o1 == m0 && j < slot);
+                                r1 += (o0 < m1) || (o0 == m1 && j <= slot);
+                                r1 += (o1 < m1) || (o1 == m1 && j < slot);
+                            }
+                        }
+                        if (slow) {
+                            const int rho = L;   // 2A > L here
+                            keep0 = r0 < rho;
+                            keep1 = r1 < rho;
+                        }
+                    }
+                }
+                const bool kill = active && !keep0 && !keep1;
+                const bool clone = keep0 && keep1;
+                const unsigned kill_all = __ballot_sync(FULL_MASK, kill);
+                const unsigned clone_all = __ballot_sync(FULL_MASK, clone);
+                if ((kill_all | clone_all) == 0) {
+                    if (active) { u = keep1 ? 1u : 0u; pm = keep1 ? m1 : m0; }
+                } else {
+                    const unsigned Kg = (kill_all >> gbase) & gmask_lo;
+                    const unsigned Cg = (clone_all >> gbase) & gmask_lo;
+                    const int nk = __popc(Kg), nc = __popc(Cg);
+                    // killPath pushes in ascending path order (PolarCode.cpp:555-560, :292)
+                    if (slot >= sp && slot < sp + nk) stk = (int)__fns(Kg, 0, slot - sp + 1);
+                    const int sp2 = sp + nk;
+                    // clonePath pops for ascending l (PolarCode.cpp:562-570, :275-276)
+                    const int ci = __popc(Cg & ((1u << slot) - 1u));
+                    const int tgt = __shfl_sync(FULL_MASK, stk, gbase + ((sp2 - 1 - ci) & (W - 1)));
+                    sp = sp2 - nc;
+                    srcof[lane] = (unsigned char)lane;
+                    __syncwarp();
+                    if (clone) srcof[gbase + tgt] = (unsigned char)lane;
+                    __syncwarp();
+                    const int src_lane = srcof[lane];
+                    __syncwarp();
+                    const bool is_new = (src_lane != lane);
+                    const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
+                    const unsigned long long src_px = __shfl_sync(FULL_MASK, px, src_lane);
+                    const unsigned long long src_ps = __shfl_sync(FULL_MASK, ps, src_lane);
+                    const uint32_t src_sn = __shfl_sync(FULL_MASK, s_n, src_lane);
+                    if (is_new) {
+                        active = true; pm = src_m1; u = 1u; px = src_px; ps = src_ps; s_n = src_sn;
+                    } else if (kill) {
+                        active = false; pm = 0.0f;
+                    } else if (active) {
+                        u = keep0 ? 0u : 1u;
+                        pm = keep0 ? m0 : m1;
+                    }
+                }
+            }
+
+            // ---- partial sums (PolarCode.cpp:457-473), bit-packed, butterfly order ----
+            if ((phi & 1) == 0) {
+                s_n = u;
+            } else {
+                const int t = __ffs(~phi) - 1;           // trailing ones of phi, 1..n
+                const int lam_end = n - t;               // layer whose S array receives the result
+                uint32_t P = u;
+                int lam = n;
+                while (lam > lam_end && (n - lam) < 5) {
+                    const int M = 1 << (n - lam);
+                    uint32_t Sw;
+                    if (lam == n) Sw = s_n;
+                    else Sw = srow(lam, 0)[get_ptr(ps, lam - 1)];
+                    P = ((Sw ^ P) & ((1u << M) - 1u)) | (P << M);
+                    --lam;
+                }
+                if (lam == lam_end) {
+                    srow(lam, 0)[lane] = P;
+                } else {
+                    const int Wd = 1 << (t - 5);          // words of the destination vector
+                    uint32_t* D = srow(lam_end, 0) + lane;
+                    D[(size_t)(Wd - 1) << 5] = P;
+                    for (; lam > lam_end; --lam) {
+                        const int mw = 1 << (n - lam - 5);
+                        const int base = Wd - mw;
+                        const uint32_t* S = srow(lam, 0) + get_ptr(ps, lam - 1);
+                        for (int w = 0; w < mw; ++w)
+                            D[(size_t)(base - mw + w) << 5] = S[(size_t)w << 5] ^ D[(size_t)(base + w) << 5];
+                    }
+                }
+                if (lam_end >= 1) ps = set_ptr(ps, lam_end - 1, lane);
+            }
+            __syncwarp();
+        }
+
+        // ---- u-hat of every path: packed polar transform of the re-encoded codeword (layer 0) ----
+        uint32_t* D = srow(0, 0) + lane;
+        for (int sw = NW >> 1; sw >= 1; sw >>= 1)
+            for (int i = 0; i < NW; ++i)
+                if ((i & sw) == 0) D[(size_t)i << 5] ^= D[(size_t)(i + sw) << 5];
+        bool pass = true;
+        {
+            // in-word stages + parity ("CRC") rows, PolarCode.cpp:93-108
+            for (int i = 0; i < NW; ++i) {
+                uint32_t w = D[(size_t)i << 5];
+                if (N > 16) w ^= (w >> 16) & 0x0000FFFFu;
+                if (N > 8) w ^= (w >> 8) & 0x00FF00FFu;
+                if (N > 4) w ^= (w >> 4) & 0x0F0F0F0Fu;
+                if (N > 2) w ^= (w >> 2) & 0x33333333u;
+                w ^= (w >> 1) & 0x55555555u;
+                D[(size_t)i << 5] = w;
+            }
+            for (int r = 0; r < a.crc; ++r) {
+                uint32_t acc = 0;
+                for (int i = 0; i < NW; ++i) acc ^= D[(size_t)i << 5] & a.crc_masks[(size_t)r * NW + i];
+                if (__popc(acc) & 1) pass = false;
+            }
+        }
+        // ---- final pick, PolarCode.cpp:609-644 ----
+        const unsigned act_all = __ballot_sync(FULL_MASK, active);
+        const unsigned pass_all = __ballot_sync(FULL_MASK, active && pass);
+        const unsigned pass_g = (pass_all >> gbase) & gmask_lo;
+        const bool use_parity = (a.crc != 0) && (pass_g != 0);
+        const bool eligible = active && (use_parity ? pass : true) && (pm < CUDART_INF_F);
+        const float best = group_min(eligible ? pm : CUDART_INF_F, W);
+        const unsigned cand_all = __ballot_sync(FULL_MASK, eligible && pm == best);
+        const unsigned cand_g = (cand_all >> gbase) & gmask_lo;
+        const int win_slot = cand_g ? (__ffs(cand_g) - 1) : 0;
+        const bool win_active = (act_all >> (gbase + win_slot)) & 1u;
+        __syncwarp();
+
+        // ---- output gather: decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174 ----
+        for (int g = 0; g < G; ++g) {
+            const int wl = __shfl_sync(FULL_MASK, gbase + win_slot, g * W);
+            const bool wa = __shfl_sync(FULL_MASK, (int)win_active, g * W);
+            const int cwg = grp * G + g;
+            if (cwg >= a.B) break;
+            const uint32_t* U = srow(0, 0) + wl;
+            for (int t = lane; t < KW; t += 32) {
+                uint32_t word = 0;
+                if (wa) {
+                    const int jmax = min(32, a.K - 32 * t);
+                    for (int i = 0; i < jmax; ++i) {
+                        const int pos = a.info_order[32 * t + i];
+                        word |= ((U[(size_t)(pos >> 5) << 5] >> (pos & 31)) & 1u) << i;
+                    }
+                }
+                a.out[(size_t)cwg * KW + t] = word;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void count_errors_kernel(const uint32_t* dec, const uint32_t* truth, int B, int KW,
+                                    uint8_t* block_err, unsigned long long* n_err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    bool err = false;
+    if (b < B) {
+        for (int w = 0; w < KW; ++w) err |= dec[(size_t)b * KW + w] != truth[(size_t)b * KW + w];
+        if (block_err) block_err[b] = err ? 1 : 0;
+    }
+    const unsigned m = __ballot_sync(FULL_MASK, err);
+    if (n_err && (threadIdx.x & 31) == 0 && m) atomicAdd(n_err, (unsigned long long)__popc(m));
+}
+
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    if (!s || !*s) return dflt;
+    return atoi(s);
+}
+
+}  // namespace
+
+struct polar_b200_ctx {
+    int device = 0;
+    int n = 0, N = 0, K = 0, crc = 0, max_list = 0, max_batch = 0;
+    int sm_count = 0;
+    int KW = 0, NW = 0;
+    uint32_t* d_frozen = nullptr;
+    uint16_t* d_order = nullptr;
+    uint32_t* d_crc_masks = nullptr;
+    float* d_gx = nullptr;
+    uint32_t* d_gs = nullptr;
+    size_t gx_stride = 0, gs_stride = 0;   // per warp, elements
+    int scratch_warps = 0;
+    int scratch_lamS = -1;
+    float* d_llr_stage = nullptr;
+    uint32_t* d_out_stage = nullptr;
+    long long launches = 0;
+    int last_wpb = 0, last_blocks = 0, last_smem = 0;
+    size_t scratch_bytes = 0;
+};
+
+namespace {
+
+#define CU_TRY(expr)                                  \
+    do {                                              \
+        cudaError_t e__ = (expr);                     \
+        if (e__ != cudaSuccess) return (int)e__;      \
+    } while (0)
+
+struct LaunchPlan {
+    int wpb, blocks, lamS, smem_x_rows, smem_s_rows, smem_bytes;
+    int s_off[kMaxN + 2];
+    size_t gx_rows, gs_rows;
+};
+
+// Decide which layers live in shared memory. Layers lamS..n-1 of the LLR tree
+// (2^(n-lamS+1) - 2 rows) and the partial-sum layers >= max(lamS,1) go to shared memory.
+LaunchPlan make_plan(const polar_b200_ctx* c) {
+    LaunchPlan p;
+    memset(&p, 0, sizeof(p));
+    const int n = c->n;
+    p.wpb = env_int("POLAR_B200_WPB", 4);
+    const int warps_per_sm = env_int("POLAR_B200_WARPS_PER_SM", 16);
+    if (p.wpb < 1) p.wpb = 1;
+    if (p.wpb > 8) p.wpb = 8;
+    int blocks_per_sm = warps_per_sm / p.wpb;
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    p.blocks = c->sm_count * blocks_per_sm;
+    const int budget_per_warp = (200 * 1024) / (blocks_per_sm * p.wpb);
+    int lamS = env_int("POLAR_B200_LAMS", -1);
+    if (lamS < 1 || lamS > n) {
+        lamS = n;   // smallest footprint, then grow while it fits
+        while (lamS > 1) {
+            const int cand = lamS - 1;
+            int xr = (1 << (n - cand + 1)) - 2;
+            int sr = 0;
+            for (int lam = (cand < 1 ? 1 : cand); lam <= n - 1; ++lam) sr += ((1 << (n - lam)) + 31) / 32;
+            if ((xr + sr) * 128 + 32 > budget_per_warp) break;
+            lamS = cand;
+        }
+    }
+    p.lamS = lamS;
+    p.smem_x_rows = (1 << (n - lamS + 1)) - 2;
+    const int lamSS = lamS < 1 ? 1 : lamS;
+    int off = 0;
+    for (int lam = 0; lam < lamSS; ++lam) { p.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
+    p.gs_rows = off;
+    off = 0;
+    for (int lam = lamSS; lam <= n - 1; ++lam) { p.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
+    p.smem_s_rows = off;
+    p.gx_rows = (size_t)(1 << n) - ((size_t)1 << (n - lamS + 1));
+    p.smem_bytes = ((p.smem_x_rows + p.smem_s_rows) * 128 + 32) * p.wpb;
+    return p;
+}
+
+int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p) {
+    const int warps = p.blocks * p.wpb;
+    if (c->d_gx && c->scratch_warps >= warps && c->scratch_lamS == p.lamS) return 0;
+    if (c->d_gx) cudaFree(c->d_gx);
+    if (c->d_gs) cudaFree(c->d_gs);
+    c->d_gx = nullptr; c->d_gs = nullptr;
+    c->gx_stride = (p.gx_rows ? p.gx_rows : 1) * 32;
+    c->gs_stride = (p.gs_rows ? p.gs_rows : 1) * 32;
+    CU_TRY(cudaMalloc(&c->d_gx, c->gx_stride * warps * sizeof(float)));
+    CU_TRY(cudaMalloc(&c->d_gs, c->gs_stride * warps * sizeof(uint32_t)));
+    c->scratch_warps = warps;
+    c->scratch_lamS = p.lamS;
+    c->scratch_bytes = (c->gx_stride * sizeof(float) + c->gs_stride * sizeof(uint32_t)) * warps;
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int polar_b200_abi_version(void) { return POLAR_B200_ABI_VERSION; }
+
+const char* polar_b200_strerror(int code) {
+    switch (code) {
+        case POLAR_B200_OK: return "ok";
+        case POLAR_B200_E_ARG: return "polar_b200: invalid argument";
+        case POLAR_B200_E_UNSUPPORTED: return "polar_b200: parameter outside what this build supports (n <= 13, list <= 32)";
+        case POLAR_B200_E_NOGPU: return "polar_b200: no usable CUDA device (there is no CPU fallback)";
+        case POLAR_B200_E_BATCH: return "polar_b200: batch larger than the ctx's max_batch";
+        case POLAR_B200_E_LIST: return "polar_b200: list size must be in 1..min(max_list, 32)";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "polar_b200: unknown error";
+}
+
+int polar_b200_info_words(int K) { return (K + 31) / 32; }
+
+int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bits,
+                      const uint8_t* frozen_mask, const uint16_t* info_order,
+                      const uint8_t* crc_matrix, int max_list, int max_batch) {
+    if (!out) return POLAR_B200_E_ARG;
+    *out = nullptr;
+    if (!frozen_mask || !info_order) return POLAR_B200_E_ARG;
+    if (n < 1 || K < 1 || crc_bits < 0 || max_batch < 1) return POLAR_B200_E_ARG;
+    if (n > kMaxN) return POLAR_B200_E_UNSUPPORTED;
+    const int N = 1 << n;
+    if (K + crc_bits > N) return POLAR_B200_E_ARG;
+    if (crc_bits > 0 && !crc_matrix) return POLAR_B200_E_ARG;
+    if (max_list < 1) return POLAR_B200_E_LIST;
+    if (max_list > 32) return POLAR_B200_E_UNSUPPORTED;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return POLAR_B200_E_NOGPU; }
+    if (device < 0 || device >= ndev) return POLAR_B200_E_ARG;
+    // consistency of the tables
+    int n_unfrozen = 0;
+    for (int i = 0; i < N; ++i) n_unfrozen += frozen_mask[i] ? 0 : 1;
+    if (n_unfrozen != K + crc_bits) return POLAR_B200_E_ARG;
+    for (int j = 0; j < K + crc_bits; ++j)
+        if (info_order[j] >= N || frozen_mask[info_order[j]]) return POLAR_B200_E_ARG;
+
+    polar_b200_ctx* c = new (std::nothrow) polar_b200_ctx;
+    if (!c) return POLAR_B200_E_ARG;
+    c->device = device; c->n = n; c->N = N; c->K = K; c->crc = crc_bits;
+    c->max_list = max_list; c->max_batch = max_batch;
+    c->KW = (K + 31) / 32; c->NW = (N + 31) / 32;
+    int rc = 0;
+    auto fail = [&](int code) { polar_b200_destroy(c); return code; };
+    if ((rc = (int)cudaSetDevice(device)) != 0) return fail(rc);
+    if ((rc = (int)cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != 0) return fail(rc);
+
+    std::vector<uint32_t> fw(c->NW, 0);
+    for (int i = 0; i < N; ++i) if (frozen_mask[i]) fw[i >> 5] |= 1u << (i & 31);
+    // parity row r over decoding positions: ones at order[j] where M[r][j] = 1, plus the
+    // parity bit's own position order[K + r] (PolarCode.cpp:95-101 rearranged to "XOR == 0").
+    std::vector<uint32_t> cm((size_t)(crc_bits ? crc_bits : 1) * c->NW, 0);
+    for (int r = 0; r < crc_bits; ++r) {
+        for (int j = 0; j < K; ++j)
+            if (crc_matrix[(size_t)r * K + j] & 1) cm[(size_t)r * c->NW + (info_order[j] >> 5)] ^= 1u << (info_order[j] & 31);
+        const int p = info_order[K + r];
+        cm[(size_t)r * c->NW + (p >> 5)] ^= 1u << (p & 31);
+    }
+    if ((rc = (int)cudaMalloc(&c->d_frozen, fw.size() * 4)) != 0) return fail(rc);
+    if ((rc = (int)cudaMalloc(&c->d_order, (size_t)(K + crc_bits) * 2)) != 0) return fail(rc);
+    if ((rc = (int)cudaMalloc(&c->d_crc_masks, cm.size() * 4)) != 0) return fail(rc);
+    if ((rc = (int)cudaMemcpy(c->d_frozen, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+    if ((rc = (int)cudaMemcpy(c->d_order, info_order, (size_t)(K + crc_bits) * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+    if ((rc = (int)cudaMemcpy(c->d_crc_masks, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+    if ((rc = (int)cudaMalloc(&c->d_llr_stage, (size_t)max_batch * N * sizeof(float))) != 0) return fail(rc);
+    if ((rc = (int)cudaMalloc(&c->d_out_stage, (size_t)max_batch * c->KW * sizeof(uint32_t))) != 0) return fail(rc);
+    *out = c;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_destroy(polar_b200_ctx* c) {
+    if (!c) return POLAR_B200_E_ARG;
+    cudaSetDevice(c->device);
+    cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
+    cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
+    delete c;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
+                              uint32_t* info_packed, void* cuda_stream) {
+    if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
+    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    LaunchPlan p = make_plan(c);
+    int rc = ensure_scratch(c, p);
+    if (rc) return rc;
+    DecodeArgs a;
+    memset(&a, 0, sizeof(a));
+    a.llr = llr; a.out = info_packed;
+    a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.gx = c->d_gx; a.gs = c->d_gs; a.gx_stride = c->gx_stride; a.gs_stride = c->gs_stride;
+    a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.L = L;
+    int W = 1; while (W < L) W <<= 1;
+    a.W = W; a.lamS = p.lamS; a.smem_x_rows = p.smem_x_rows; a.smem_s_rows = p.smem_s_rows;
+    memcpy(a.s_off, p.s_off, sizeof(a.s_off));
+    const int G = 32 / W;
+    const int groups = (B + G - 1) / G;
+    int blocks = p.blocks;
+    const int need_blocks = (groups + p.wpb - 1) / p.wpb;
+    if (blocks > need_blocks) blocks = need_blocks;
+    CU_TRY(cudaFuncSetAttribute(scl_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    scl_decode_kernel<<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int B, int L,
+                                   uint32_t* info_packed_host, void* cuda_stream) {
+    if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
+    if (B > c->max_batch) return POLAR_B200_E_BATCH;
+    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, st));
+    int rc = polar_b200_decode_scl_llr(c, c->d_llr_stage, B, L, c->d_out_stage, cuda_stream);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return POLAR_B200_OK;
+}
+
+int polar_b200_count_errors(polar_b200_ctx* c, const uint32_t* info_packed, const uint32_t* truth_packed,
+                            int B, uint8_t* block_err, unsigned long long* n_err, void* cuda_stream) {
+    if (!c || !info_packed || !truth_packed || B < 0) return POLAR_B200_E_ARG;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    count_errors_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(info_packed, truth_packed, B, c->KW, block_err, n_err);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return POLAR_B200_OK;
+}
+
+long long polar_b200_get_info(polar_b200_ctx* c, int key) {
+    if (!c) return -1;
+    switch (key) {
+        case POLAR_B200_INFO_KERNEL_LAUNCHES: return c->launches;
+        case POLAR_B200_INFO_SM_COUNT: return c->sm_count;
+        case POLAR_B200_INFO_WARPS_PER_BLOCK: return c->last_wpb;
+        case POLAR_B200_INFO_BLOCKS: return c->last_blocks;
+        case POLAR_B200_INFO_SMEM_BYTES: return c->last_smem;
+        case POLAR_B200_INFO_SCRATCH_BYTES: return (long long)c->scratch_bytes;
+        default: return -1;
+    }
+}
+
+}  // extern "C"
