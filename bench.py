@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""bench.py -- codewords/s of the LLR-domain SCL polar decoder (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c2|c3|c5]
+
+A "step" is one pass of the hot path (decode_scl_llr) over one batch of synthetic BPSK/AWGN
+codewords. Default workload = BASELINE.json configs[3], the one the metric is quoted on:
+N=2048, K=1024, 16 parity ("CRC") bits, list 32, Eb/N0 swept 1.0-2.5 dB (the sweep points are
+interleaved over the batch), 65536 codewords per GPU; the batch shards over ranks with no
+data-path collective (weak scaling) and only the block-error counters are all-reduced.
+
+One JSON line on rank 0. `value` = whole-job codewords/s with LLRs resident in HBM (CUDA events on
+the launch stream, max over ranks); `e2e` = the same through the C ABI's host entry point
+(pinned host LLRs -> H2D -> decode -> D2H of the packed bits, every step); `roofline` = the
+decode kernel against the measured HBM copy bandwidth with SURVEY.md section 8(d)'s algorithmic bytes
+(4N + ceil(K/8) per codeword); `cpu_baseline` = the unmodified reference (oracle/_ref) or its port
+timed on this box's host cores on a bounded sample of the same workload.
+
+`--impl reference` times that CPU implementation instead (rank 0 only, all host threads, each
+step a bounded sample of the same workload).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (n, K, crc, L, sweep of Eb/N0 in dB, BASELINE.json index)
+    "c2": (11, 1024, 0, 1, (2.0,), 1),
+    "c3": (11, 1024, 16, 4, (2.0,), 2),
+    "c4": (11, 1024, 16, 32, (1.0, 1.25, 1.5, 1.75, 2.0, 2.25, 2.5), 3),
+    "c5": (9, 256, 0, 32, (2.0,), 4),
+}
+SEED = 0x5EED0000
+
+
+def workload_name(cfg, batch):
+    n, K, crc, L, sweep, idx = CONFIGS[cfg]
+    return "configs[%d]: N=%d K=%d crc=%d L=%d SCL-LLR, Eb/N0 %s dB, batch=%d codewords/GPU" % (
+        idx, 1 << n, K, crc, L, "%.2f-%.2f sweep" % (sweep[0], sweep[-1]) if len(sweep) > 1 else "%.2f" % sweep[0], batch)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_decoder(n, K, crc):
+    """(kind, object with decode_batch(llr, L, nthreads)) -- the compiled reference when it was prebuilt."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    if oracle_lib.have_ref():
+        return "reference", oracle_lib.Ref(n, K, 0.32, crc)
+    return "port", oracle_lib.Port(n, K, 0.32, crc)
+
+
+def time_cpu(dec, llr, L, threads, budget_s):
+    """decode a bounded sample sized for ~budget_s seconds; returns (cw/s, sample size)."""
+    probe = min(len(llr), max(threads, 8))
+    t0 = time.perf_counter(); dec.decode_batch(llr[:probe], L, threads); t = time.perf_counter() - t0
+    rate = probe / max(t, 1e-6)
+    S = int(min(len(llr), max(threads, rate * budget_s)))
+    S = max(threads, (S // threads) * threads)
+    t0 = time.perf_counter(); dec.decode_batch(llr[:S], L, threads); t = time.perf_counter() - t0
+    return S / t, S
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from polar_b200 import synth
+    n, K, crc, L, sweep, _ = CONFIGS[args.config]
+    kind, dec = cpu_decoder(n, K, crc)
+    threads = os.cpu_count() or 1
+    # sample sized so that warmup + steps finish in about two minutes
+    per_step_s = max(1.0, 120.0 / (args.steps + args.warmup))
+    info, llr = synth.make_shard(dec, SEED, 0, 4 * synth.BLOCK, sweep=sweep)
+    probe = max(threads, 8)
+    t0 = time.perf_counter(); dec.decode_batch(llr[:probe], L, threads); rate = probe / (time.perf_counter() - t0)
+    S = int(min(len(llr), max(threads, rate * per_step_s)))
+    S = max(threads, (S // threads) * threads)
+    for _ in range(args.warmup):
+        dec.decode_batch(llr[:S], L, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = dec.decode_batch(llr[:S], L, threads)
+    dt = time.perf_counter() - t0
+    value = S * args.steps / dt
+    sample = "%d codewords/step of the same workload, %d host threads, %s" % (
+        S, threads, "unmodified PolarC/PolarCode.cpp -O2 (oracle/_ref)" if kind == "reference" else "oracle port -O2")
+    print(json.dumps({
+        "impl": "reference", "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.config, args.batch), "sample_per_step": S},
+        "cpu_baseline": {"value": value, "unit": "codewords/s", "cores": threads, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "codewords/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "bler": float((out != info[:S]).any(1).mean()),
+    }), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from polar_b200 import PolarCode, bler, synth
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- polar_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, K, crc, L, sweep, _ = CONFIGS[args.config]
+    N, B = 1 << n, args.batch
+    code = PolarCode(n, K, 0.32, crc, device=local)
+    KW = code.KW
+
+    # this rank's shard of the global batch (weak scaling: B codewords per GPU), pinned on the host
+    h_llr = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
+    h_out = torch.empty((B, KW), dtype=torch.int32, pin_memory=True)
+    info, _ = synth.make_shard(code, SEED, rank * B, B, sweep=sweep, out_llr=h_llr.numpy())
+    from polar_b200 import pack_bits
+    d_truth = torch.from_numpy(pack_bits(info).view(np.int32)).to(dev)
+    d_llr = h_llr.to(dev)
+    d_out = torch.empty((B, KW), dtype=torch.int32, device=dev)
+    d_nerr = torch.zeros(1, dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident arm ----
+    for _ in range(args.warmup):
+        code.decode_device(d_llr, L, out=d_out)
+    launches0 = code.kernel_launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        code.decode_device(d_llr, L, out=d_out)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = code.kernel_launches - launches0
+    code.count_errors(d_out, d_truth, None, d_nerr)
+    torch.cuda.synchronize(dev)
+
+    # ---- end-to-end arm: pinned host LLRs in, packed bits out, through the C ABI host entry ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    code.decode_batch(h_llr, L, packed=True, out=h_out)      # warm (allocates the staging buffers)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        code.decode_batch(h_llr, L, packed=True, out=h_out)
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    e2e_ok = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
+
+    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
+    counts = np.array([[[int(d_nerr.item()), B]]], np.int64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        counts = bler.all_reduce_counts(counts, dev)
+    ms, e2e_s = float(t[0].item()), float(t[1].item())
+
+    if rank == 0:
+        ms_step = ms / args.steps
+        value = world * B * args.steps / (ms * 1e-3)
+        bytes_cw = 4 * N + (K + 7) // 8
+        peak, peak_src = measured_peak()
+        achieved = B * bytes_cw / (ms_step * 1e-3) / 1e9     # per GPU: one launch decodes this rank's B codewords
+        out = {
+            "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config, B), "global_batch": world * B,
+                       "l2": "input %d MiB per GPU per step > 126 MB L2, no flush needed" % (B * N * 4 >> 20),
+                       "sharding": "contiguous codeword blocks per rank, no data-path collective; counters all-reduced"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_codeword": bytes_cw,
+                         "kernel": "scl_decode_kernel", "kernel_ms": ms_step},
+            "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "codewords/s", "h2d_bytes_per_step": B * N * 4,
+                    "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "bler": float(counts[0, 0, 0] / counts[0, 0, 1]),
+        }
+        if world == 1 and not args.no_cpu:
+            kind, dec = cpu_decoder(n, K, crc)
+            threads = os.cpu_count() or 1
+            v, S = time_cpu(dec, h_llr.numpy(), L, threads, args.cpu_seconds)
+            out["cpu_baseline"] = {
+                "value": v, "unit": "codewords/s", "cores": threads, "kind": kind,
+                "sample": "first %d codewords of the same batch, %s, g++ -O2, one decoder object per thread" % (
+                    S, "unmodified PolarC/PolarCode.cpp (oracle/_ref)" if kind == "reference" else "oracle port")}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=65536, help="codewords per GPU per step")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -64,7 +64,7 @@ int polar_b200_info_words(int K);
  * (Bhattacharyya recursion, std::sort, rand() parity matrix) stays on the host
  * C++ side and is passed in as data, so this library is independent of
  * rand()/std::sort quirks:
- *   n            log2 of the block length N, 1 <= n <= 12
+ *   n            log2 of the block length N, 1 <= n <= 13
  *   K            info bits; crc_bits parity ("CRC") bits, K + crc_bits <= N
  *   frozen_mask  [N] bytes, 1 = frozen, index = decoding position phi (_frozen_bits)
  *   info_order   [K + crc_bits] = prefix of _channel_order_descending: position of info
@@ -116,7 +116,8 @@ enum {
     POLAR_B200_INFO_WARPS_PER_BLOCK = 2, /* of the last decode launch                       */
     POLAR_B200_INFO_BLOCKS = 3,          /* grid size of the last decode launch             */
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
-    POLAR_B200_INFO_SCRATCH_BYTES = 5    /* device scratch owned by the ctx                 */
+    POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
+    POLAR_B200_INFO_KERNEL_KIND = 6      /* last decode: 0 = generic kernel, 1 + i = fast variant i */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
 

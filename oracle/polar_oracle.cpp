@@ -37,6 +37,9 @@
 
 namespace {
 
+// instrumentation (single-threaded use only): info steps, info steps with >= 1 clone, clones, kills
+long long g_stats[4] = {0, 0, 0, 0};
+
 struct Code {
     int n = 0, N = 0, K = 0, crc = 0;
     double eps = 0.0;
@@ -247,6 +250,14 @@ struct Decoder {
             if (fork[i] > thr) { keep[i] = 1; ++kept; }
         for (int i = 0; i < 2 * L && kept < rho; ++i)                         // :543-553
             if (fork[i] == thr) { keep[i] = 1; ++kept; }
+        {
+            int nclone = 0, nkill = 0;
+            for (int l = 0; l < L; ++l) {
+                if (alive[l] && keep[2 * l] && keep[2 * l + 1]) ++nclone;
+                if (alive[l] && !keep[2 * l] && !keep[2 * l + 1]) ++nkill;
+            }
+            g_stats[0] += 1; g_stats[1] += (nclone > 0); g_stats[2] += nclone; g_stats[3] += nkill;
+        }
         for (int l = 0; l < L; ++l)                                           // :555-560
             if (alive[l] && !keep[2 * l] && !keep[2 * l + 1]) kill(l);
         for (int l = 0; l < L; ++l) {                                         // :562-605
@@ -360,6 +371,9 @@ void* oracle_create_from_tables(int n, int K, int crc, const uint8_t* frozen, co
 }
 
 void oracle_destroy(void* h) { delete static_cast<Code*>(h); }
+
+// read-and-reset the instrumentation counters (meaningful after single-threaded decodes only)
+void oracle_stats(long long* out4) { for (int i = 0; i < 4; ++i) { out4[i] = g_stats[i]; g_stats[i] = 0; } }
 
 void oracle_get_construction(void* h, uint8_t* frozen, uint16_t* order, uint8_t* crc_matrix, uint16_t* bitrev) {
     const Code& c = *static_cast<Code*>(h);

@@ -120,6 +120,12 @@ __device__ __forceinline__ unsigned long long set_ptr(unsigned long long p, int 
 }
 __device__ __forceinline__ int get_ptr(unsigned long long p, int idx) { return (int)((p >> (5 * idx)) & 31ull); }
 
+}  // namespace
+
+#include "scl_fast.cuh"
+
+namespace {
+
 // One warp decodes groups of 32/W codewords. Dynamic shared memory per warp:
 //   smem_x_rows rows of 32 floats (LLR layers lamS..n-1), smem_s_rows rows of 32 words
 //   (partial-sum layers >= max(lamS,1), except layer n which is a register), 32 bytes of scatter
@@ -437,8 +443,11 @@ struct polar_b200_ctx {
     int scratch_lamS = -1;
     float* d_llr_stage = nullptr;
     uint32_t* d_out_stage = nullptr;
+    float* d_fgx = nullptr;                // scratch of the fast kernel
+    uint32_t* d_fgs = nullptr;
+    int fast_variant = -1, fast_warps = 0;
     long long launches = 0;
-    int last_wpb = 0, last_blocks = 0, last_smem = 0;
+    int last_wpb = 0, last_blocks = 0, last_smem = 0, last_kernel = 0;
     size_t scratch_bytes = 0;
 };
 
@@ -510,6 +519,77 @@ int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p) {
     c->scratch_lamS = p.lamS;
     c->scratch_bytes = (c->gx_stride * sizeof(float) + c->gs_stride * sizeof(uint32_t)) * warps;
     return 0;
+}
+
+// ---- fast-kernel variants (scl_fast.cuh) ----
+struct FastVariant {
+    int nlog, T, lamS, wpb, bps;
+    size_t gx_floats, gs_words;
+    int smem_per_warp;
+    void (*launch)(const fast::Args&, int blocks, cudaStream_t st);
+    cudaError_t (*prepare)();
+};
+
+template <class C, int WPB, int BPS>
+void launch_fast(const fast::Args& a, int blocks, cudaStream_t st) {
+    fast::scl_fast_kernel<C, WPB, BPS><<<blocks, WPB * 32, C::SMEM_PER_WARP * WPB, st>>>(a);
+}
+template <class C, int WPB, int BPS>
+cudaError_t prepare_fast() {
+    return cudaFuncSetAttribute(fast::scl_fast_kernel<C, WPB, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                C::SMEM_PER_WARP * WPB);
+}
+#define POLAR_FAST(NLOG, T, LAMS, WPB, BPS)                                                              \
+    { NLOG, T, LAMS, WPB, BPS, fast::Cfg<NLOG, T, LAMS>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS>::GS_WORDS,   \
+      fast::Cfg<NLOG, T, LAMS>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS>,           \
+      prepare_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS> }
+
+// first match for a given n is the default; POLAR_B200_FAST_VARIANT=<index> overrides
+const FastVariant kFastVariants[] = {
+    POLAR_FAST(11, 3, 5, 4, 3),    // 0: N=2048, layers 3-4 in HBM scratch, 12 warps/SM
+    POLAR_FAST(11, 3, 6, 4, 5),    // 1: N=2048, layers 3-5 in HBM scratch, 20 warps/SM
+    POLAR_FAST(9, 3, 3, 4, 3),     // 2: N=512, everything per-path in shared memory, 12 warps/SM
+    POLAR_FAST(9, 3, 4, 4, 5),     // 3: N=512, layer 3 in HBM scratch, 20 warps/SM
+    POLAR_FAST(10, 3, 4, 4, 3),    // 4: N=1024
+    POLAR_FAST(12, 3, 6, 4, 3),    // 5: N=4096
+    POLAR_FAST(8, 3, 3, 4, 4),     // 6: N=256
+};
+constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
+
+int pick_fast_variant(int n, int L) {
+    if (env_int("POLAR_B200_FORCE_GENERIC", 0)) return -1;
+    if (L <= env_int("POLAR_B200_FAST_MIN_L", 16)) return -1;   // smaller lists: several codewords per warp (generic kernel)
+    const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
+    if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n) return forced;
+    for (int i = 0; i < kNumFastVariants; ++i)
+        if (kFastVariants[i].nlog == n) return i;
+    return -1;
+}
+
+int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st) {
+    const FastVariant& v = kFastVariants[variant];
+    int blocks = c->sm_count * v.bps;
+    const int warps = blocks * v.wpb;
+    if (c->fast_variant != variant || c->fast_warps < warps) {
+        if (c->d_fgx) cudaFree(c->d_fgx);
+        if (c->d_fgs) cudaFree(c->d_fgs);
+        c->d_fgx = nullptr; c->d_fgs = nullptr;
+        CU_TRY(cudaMalloc(&c->d_fgx, v.gx_floats * warps * sizeof(float)));
+        CU_TRY(cudaMalloc(&c->d_fgs, v.gs_words * warps * sizeof(uint32_t)));
+        CU_TRY(v.prepare());
+        c->fast_variant = variant; c->fast_warps = warps;
+        c->scratch_bytes = (v.gx_floats * sizeof(float) + v.gs_words * sizeof(uint32_t)) * warps;
+    }
+    fast::Args a;
+    a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.gx = c->d_fgx; a.gs = c->d_fgs; a.B = B; a.K = c->K; a.crc = c->crc; a.L = L;
+    const int need = (B + v.wpb - 1) / v.wpb;
+    if (blocks > need) blocks = need;
+    v.launch(a, blocks, st);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    c->last_wpb = v.wpb; c->last_blocks = blocks; c->last_smem = v.smem_per_warp * v.wpb; c->last_kernel = 1 + variant;
+    return POLAR_B200_OK;
 }
 
 }  // namespace
@@ -595,6 +675,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaSetDevice(c->device);
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
+    cudaFree(c->d_fgx); cudaFree(c->d_fgs);
     delete c;
     return POLAR_B200_OK;
 }
@@ -606,6 +687,8 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    const int fv = pick_fast_variant(c->n, L);
+    if (fv >= 0) return decode_fast(c, fv, llr, B, L, info_packed, st);
     LaunchPlan p = make_plan(c);
     int rc = ensure_scratch(c, p);
     if (rc) return rc;
@@ -627,7 +710,7 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
     scl_decode_kernel<<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
-    c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes;
+    c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes; c->last_kernel = 0;
     return POLAR_B200_OK;
 }
 
@@ -667,6 +750,7 @@ long long polar_b200_get_info(polar_b200_ctx* c, int key) {
         case POLAR_B200_INFO_BLOCKS: return c->last_blocks;
         case POLAR_B200_INFO_SMEM_BYTES: return c->last_smem;
         case POLAR_B200_INFO_SCRATCH_BYTES: return (long long)c->scratch_bytes;
+        case POLAR_B200_INFO_KERNEL_KIND: return c->last_kernel;
         default: return -1;
     }
 }

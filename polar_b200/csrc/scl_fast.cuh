@@ -1,0 +1,499 @@
+// scl_fast.cuh -- the throughput kernel: list sizes 17..32 (and smaller lists run on 32 lanes),
+// block lengths 2^8..2^12, one codeword per warp, lane = list path.
+//
+// Same algorithm and the same arithmetic contract as the generic kernel in polar_b200.cu (the
+// reference's decode_scl_llr, PolarC/PolarCode.cpp:130-190, 422-644). What differs is purely where
+// data lives and how much code runs per tree node:
+//
+//   * everything is a template of (NLOG, T, LAMS): layer sizes, row offsets and memory spaces are
+//     compile-time constants and the per-bit descent is a jump into straight-line code;
+//   * the TOP T layers of the LLR tree -- 1 - 2^-T of all per-path bytes -- are never stored per
+//     path. Their f-only prefixes are computed once while a single path exists (shared, compact
+//     arrays XS_1..XS_T), and every other node of layer T is recomputed on the fly from the
+//     channel LLRs (or from a shared array) and the path's own partial-sum bits: a g node costs one
+//     add, and the few f nodes that get evaluated twice add about 5% to the f count at T = 3.
+//     Per-path storage therefore starts at layer T: N/2^T rows instead of N;
+//   * layers T..LAMS-1 go to a per-warp scratch in HBM that is small enough to stay L2-resident,
+//     layers LAMS..NLOG-1 to shared memory, layer NLOG is a register;
+//   * partial sums of the five deepest layers are one packed register per lane (cloning a path =
+//     one shuffle); the larger ones are packed words [word][lane] behind 5-bit column pointers;
+//   * the 2L -> L prune is "promote the best unlikely fork, demote the worst likely fork, until
+//     the best unlikely fork no longer beats the worst likely one", two warp REDUX per round;
+//     its first round is the common no-fork-survives exit. It yields exactly the reference's
+//     sort / threshold / index-order selection (PolarCode.cpp:528-553).
+#pragma once
+
+namespace fast {
+
+template <int NLOG_, int T_, int LAMS_>
+struct Cfg {
+    static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_;
+    static constexpr int N = 1 << NLOG;
+    static constexpr int MT = N >> T;                 // rows of the first per-path layer
+    static constexpr int NW = N / 32;
+    static_assert(NLOG - T >= 5, "layer T must have at least 32 rows");
+    static_assert(LAMS >= T && LAMS <= NLOG, "bad shared-memory split");
+    // rows of per-path layers [a, b)
+    static constexpr __host__ __device__ int rows(int a, int b) { return (N >> (a - 1)) - (N >> (b - 1)); }
+    static constexpr int GX_ROWS = rows(T, LAMS);      // HBM scratch rows (32 floats each)
+    static constexpr int SX_ROWS = rows(LAMS, NLOG);   // shared rows
+    static constexpr int XS_FLOATS = N - MT;           // shared compact arrays XS_1..XS_T
+    static constexpr __host__ __device__ int xs_off(int lev) { return N - (N >> (lev - 1)); }   // XS_lev at this float offset
+    // partial-sum word layers: 1..NLOG-5 (>= 32 bits). Layers with >= 16 words live in HBM scratch.
+    static constexpr int SWL = NLOG - 5;               // last word layer
+    static constexpr __host__ __device__ int swords(int lam) { return (N >> lam) / 32; }
+    static constexpr __host__ __device__ bool s_global(int lam) { return lam == 0 || swords(lam) >= 16; }
+    static constexpr __host__ __device__ int s_off(int lam) {              // row offset within its space
+        int off = 0;
+        for (int j = 0; j < lam; ++j)
+            if (s_global(j) == s_global(lam)) off += (j == 0 ? NW : swords(j));
+        return off;
+    }
+    static constexpr __host__ __device__ int gs_rows() { int r = NW; for (int j = 1; j <= SWL; ++j) if (s_global(j)) r += swords(j); return r; }
+    static constexpr __host__ __device__ int ss_rows() { int r = 0; for (int j = 1; j <= SWL; ++j) if (!s_global(j)) r += swords(j); return r; }
+    static constexpr int GS_ROWS = gs_rows();
+    static constexpr int SS_ROWS = ss_rows();
+    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 32;
+    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + XS_FLOATS;
+    static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
+};
+
+struct Args {
+    const float* llr;
+    uint32_t* out;
+    const uint32_t* frozen_words;
+    const uint16_t* info_order;
+    const uint32_t* crc_masks;
+    float* gx;
+    uint32_t* gs;
+    int B, K, crc, L;
+};
+
+struct Warp {          // per-warp pointers
+    float* sx;         // shared LLR rows
+    uint32_t* ss;      // shared partial-sum rows
+    unsigned char* srcof;
+    float* gx;         // HBM LLR rows, followed by XS
+    float* xs;         // shared compact arrays
+    uint32_t* gs;      // HBM partial-sum rows
+    const float* chan;
+    int lane;
+};
+
+struct Lane {          // per-path state
+    float pm;
+    bool active;
+    unsigned long long px;   // column pointers of LLR layers T.. (index lam - T)
+    unsigned long long ps;   // column pointers of partial-sum word layers 1..SWL (index lam - 1)
+    uint32_t sreg;           // packed partial sums of layers NLOG-k, k = 0..4, at bit 2^k - 1
+    int stk;                 // free-path stack entry held by this lane
+};
+
+__device__ __forceinline__ unsigned brev_bits(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
+constexpr __host__ __device__ unsigned cbrev(unsigned x, int bits) {
+    unsigned r = 0;
+    for (int b = 0; b < bits; ++b) if (x & (1u << b)) r |= 1u << (bits - 1 - b);
+    return r;
+}
+constexpr __host__ __device__ int lead_zeros(int node, int bits) {
+    int z = 0;
+    for (int b = bits - 1; b >= 0; --b) { if (node & (1 << b)) break; ++z; }
+    return z;
+}
+
+template <class C, int LAM>
+__device__ __forceinline__ float* xbase(const Warp& w) {
+    if constexpr (LAM >= C::LAMS) return w.sx + C::rows(C::LAMS, LAM) * 32;
+    else return w.gx + C::rows(C::T, LAM) * 32;
+}
+template <class C, int LAM>
+__device__ __forceinline__ uint32_t* sbase(const Warp& w) {
+    if constexpr (C::s_global(LAM)) return w.gs + C::s_off(LAM) * 32;
+    else return w.ss + C::s_off(LAM) * 32;
+}
+template <class C>
+__device__ __forceinline__ uint32_t* sbase_rt(const Warp& w, int lam) {
+    uint32_t* p = nullptr;
+#define POLAR_SB(L_) if constexpr (L_ <= C::SWL) { if (lam == L_) p = sbase<C, L_>(w); }
+    POLAR_SB(0) POLAR_SB(1) POLAR_SB(2) POLAR_SB(3) POLAR_SB(4) POLAR_SB(5) POLAR_SB(6) POLAR_SB(7) POLAR_SB(8)
+#undef POLAR_SB
+    return p;
+}
+
+__device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
+    // (1 - 2u) a + b, PolarCode.cpp:448-451
+    return b + __int_as_float(__float_as_int(a) ^ (int)(bit << 31));
+}
+
+// ---- one per-path layer: X_LAM = f / g (X_{LAM-1}) ----
+template <class C, int LAM, bool ISG>
+__device__ __forceinline__ void layer_step(const Warp& w, Lane& s, float& lam_n) {
+    constexpr int M = C::N >> LAM;
+    constexpr int NLOG = C::NLOG;
+    const float* src = xbase<C, LAM - 1>(w) + get_ptr(s.px, LAM - 1 - C::T);
+    if (s.active) {
+        if constexpr (M >= 32) {
+            float* dst = xbase<C, LAM>(w) + w.lane;
+            const uint32_t* sw = nullptr;
+            if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
+#pragma unroll 1
+            for (int wd = 0; wd < M / 32; ++wd) {
+                uint32_t word = 0;
+                if constexpr (ISG) word = sw[wd * 32];
+#pragma unroll 2
+                for (int i0 = 0; i0 < 32; i0 += 4) {
+                    float a[4], b[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        a[j] = src[(wd * 32 + i0 + j) * 32];
+                        b[j] = src[(wd * 32 + i0 + j + M) * 32];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float y;
+                        if constexpr (ISG) y = g_rule(a[j], b[j], (word >> (i0 + j)) & 1u);
+                        else y = f_rule(a[j], b[j]);
+                        dst[(wd * 32 + i0 + j) * 32] = y;
+                    }
+                }
+            }
+        } else {
+            // small layers: fully unrolled, partial sums from the packed register
+            constexpr int k = NLOG - LAM;                 // M = 2^k
+            const uint32_t field = s.sreg >> ((1 << k) - 1);
+            float a[M], b[M];
+#pragma unroll
+            for (int j = 0; j < M; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
+#pragma unroll
+            for (int j = 0; j < M; ++j) {
+                float y;
+                if constexpr (ISG) y = g_rule(a[j], b[j], (field >> j) & 1u);
+                else y = f_rule(a[j], b[j]);
+                if constexpr (LAM == NLOG) lam_n = y;
+                else (xbase<C, LAM>(w) + w.lane)[j * 32] = y;
+            }
+        }
+    }
+    if constexpr (LAM < NLOG) s.px = set_ptr(s.px, LAM - C::T, w.lane);
+}
+
+// ---- layer T node NODE (1 .. 2^T - 1) for every path, from the channel / shared arrays ----
+template <class C, int NODE>
+__device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
+    constexpr int T = C::T, MT = C::MT, NLOG = C::NLOG;
+    constexpr int S0 = lead_zeros(NODE, T);          // values enter at level S0 (0 = channel)
+    constexpr int CNT = 1 << (T - S0);
+    float* dst = xbase<C, T>(w) + w.lane;
+    if (s.active) {
+#pragma unroll 1
+        for (int wd = 0; wd < MT / 32; ++wd) {
+            // partial-sum words of this path for the g levels: level lev, local element i sits at
+            // position beta + MT * brev(i) of layer lev
+            uint32_t sw[T + 1][CNT / 2 > 0 ? CNT / 2 : 1];
+#pragma unroll
+            for (int lev = S0 + 1; lev <= T; ++lev) {
+                if ((NODE >> (T - lev)) & 1) {
+                    const uint32_t* base = sbase_rt<C>(w, lev) + get_ptr(s.ps, lev - 1);
+#pragma unroll
+                    for (int i = 0; i < (1 << (T - lev)); ++i)
+                        sw[lev][i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
+                }
+            }
+#pragma unroll 2
+            for (int bi = 0; bi < 32; ++bi) {
+                const int beta = wd * 32 + bi;
+                float v[CNT];
+                if constexpr (S0 == 0) {
+                    const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(beta, NLOG - T));
+#pragma unroll
+                    for (int q = 0; q < CNT / 4; ++q) {
+                        const float4 t4 = __ldg(c4 + q);
+                        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                    }
+                } else {
+                    const float* xs = w.xs + C::xs_off(S0);
+#pragma unroll
+                    for (int i = 0; i < CNT; ++i) v[i] = xs[beta + MT * (int)cbrev(i, T - S0)];
+                }
+#pragma unroll
+                for (int lev = S0 + 1; lev <= T; ++lev) {
+                    const bool isg = (NODE >> (T - lev)) & 1;
+#pragma unroll
+                    for (int i = 0; i < (1 << (T - lev)); ++i) {
+                        if (isg) v[i] = g_rule(v[2 * i], v[2 * i + 1], (sw[lev][i] >> bi) & 1u);
+                        else v[i] = f_rule(v[2 * i], v[2 * i + 1]);
+                    }
+                }
+                dst[beta * 32] = v[0];
+            }
+        }
+    }
+    s.px = set_ptr(s.px, 0, w.lane);
+}
+
+// ---- node 0 of layer T: one path exists, the warp works across beta; fills XS_1..XS_T ----
+template <class C>
+__device__ __forceinline__ void top_solo(const Warp& w, Lane& s, int c0) {
+    constexpr int T = C::T, N = C::N, NLOG = C::NLOG;
+    float* xs1 = w.xs + C::xs_off(1);
+    for (int k = w.lane; k < N / 2; k += 32) {
+        const float2 c = __ldg(reinterpret_cast<const float2*>(w.chan) + k);
+        xs1[brev_bits(k, NLOG - 1)] = f_rule(c.x, c.y);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int lev = 2; lev <= T; ++lev) {
+        const float* in = w.xs + C::xs_off(lev - 1);
+        float* out = w.xs + C::xs_off(lev);
+        const int M = N >> lev;
+        for (int b = w.lane; b < M; b += 32) out[b] = f_rule(in[b], in[b + M]);
+        __syncwarp();
+    }
+    const float* xt = w.xs + C::xs_off(T);
+    float* col = xbase<C, T>(w) + c0;
+    for (int b = w.lane; b < C::MT; b += 32) col[b * 32] = xt[b];
+    __syncwarp();
+    s.px = set_ptr(s.px, 0, c0);
+}
+
+template <class C, int LAM>
+__device__ __forceinline__ void f_chain(const Warp& w, Lane& s, float& lam_n) {
+    layer_step<C, LAM, false>(w, s, lam_n);
+    if constexpr (LAM < C::NLOG) f_chain<C, LAM + 1>(w, s, lam_n);
+}
+
+template <class C>
+__device__ __forceinline__ void descend(const Warp& w, Lane& s, float& lam_n, int phi, int c0) {
+    constexpr int T = C::T, NLOG = C::NLOG;
+    const int lam_top = (phi == 0) ? 0 : NLOG - (__ffs(phi) - 1);
+    bool first = true;
+    if (lam_top <= T) {
+        const int node = phi >> (NLOG - T);
+        switch (node) {
+            case 0: top_solo<C>(w, s, c0); break;
+#define POLAR_TN(N_) case N_: if constexpr (N_ < (1 << T)) top_node<C, N_>(w, s); break;
+            POLAR_TN(1) POLAR_TN(2) POLAR_TN(3) POLAR_TN(4) POLAR_TN(5) POLAR_TN(6) POLAR_TN(7)
+            POLAR_TN(8) POLAR_TN(9) POLAR_TN(10) POLAR_TN(11) POLAR_TN(12) POLAR_TN(13) POLAR_TN(14) POLAR_TN(15)
+#undef POLAR_TN
+            default: break;
+        }
+        first = false;
+    }
+    const int entry = (lam_top <= T) ? T + 1 : lam_top;
+    switch (entry) {
+#define POLAR_LS(L_)                                                                           \
+    case L_:                                                                                   \
+        if constexpr (L_ > T && L_ <= NLOG) {                                                  \
+            if (first) layer_step<C, L_, true>(w, s, lam_n);                                   \
+            else layer_step<C, L_, false>(w, s, lam_n);                                        \
+            first = false;                                                                     \
+        }                                                                                      \
+        [[fallthrough]];
+        POLAR_LS(2) POLAR_LS(3) POLAR_LS(4) POLAR_LS(5) POLAR_LS(6) POLAR_LS(7) POLAR_LS(8) POLAR_LS(9)
+        POLAR_LS(10) POLAR_LS(11) POLAR_LS(12) POLAR_LS(13)
+#undef POLAR_LS
+        default: break;
+    }
+}
+
+// ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607), 32 lanes = one codeword ----
+// Returns the decided bit of this lane's (possibly new) path.
+template <class C>
+__device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp) {
+    const int lane = w.lane;
+    const float m0 = s.pm + softplus_ref(-lam_n);
+    const float m1 = s.pm + softplus_ref(lam_n);
+    const unsigned act = __ballot_sync(FULL_MASK, s.active);
+    const int A = __popc(act);
+    bool keep0 = s.active, keep1 = s.active;
+    if (2 * A > L) {
+        // keep the L best forks under (metric asc, fork index asc)
+        const bool like1 = m1 < m0;                        // likely fork is bit 1
+        const unsigned lk = __ballot_sync(FULL_MASK, like1);
+        const unsigned klo = __float_as_uint(like1 ? m1 : m0);   // metrics are >= 0: uint order = float order
+        const unsigned khi = __float_as_uint(like1 ? m0 : m1);
+        unsigned keptA = act, keptB = 0;
+        int count = A;
+        while (true) {
+            const unsigned candB = act & ~keptB;
+            if (candB == 0) break;
+            const unsigned kb = __reduce_min_sync(FULL_MASK, ((candB >> lane) & 1u) ? khi : 0xFFFFFFFFu);
+            const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
+            const int bl = __ffs(eqb) - 1;                 // lowest lane = lowest fork index among equals
+            if (count < L) { keptB |= 1u << bl; ++count; continue; }
+            const unsigned ka = __reduce_max_sync(FULL_MASK, ((keptA >> lane) & 1u) ? klo : 0u);
+            const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
+            const int al = 31 - __clz(eqa);                // highest lane = highest fork index among equals
+            const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
+            const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
+            const bool better = (kb < ka) || (kb == ka && idxb < idxa);
+            if (!better) break;
+            keptB |= 1u << bl;
+            keptA &= ~(1u << al);
+        }
+        const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
+        keep0 = like1 ? kb_ : ka_;
+        keep1 = like1 ? ka_ : kb_;
+    }
+    const bool kill = s.active && !keep0 && !keep1;
+    const bool clone = keep0 && keep1;
+    const unsigned Kg = __ballot_sync(FULL_MASK, kill);
+    const unsigned Cg = __ballot_sync(FULL_MASK, clone);
+    uint32_t u = 0;
+    if ((Kg | Cg) == 0) {
+        if (s.active) { u = keep1 ? 1u : 0u; s.pm = keep1 ? m1 : m0; }
+        return u;
+    }
+    const int nk = __popc(Kg), nc = __popc(Cg);
+    if (lane >= sp && lane < sp + nk) s.stk = (int)__fns(Kg, 0, lane - sp + 1);   // kills pushed ascending
+    const int sp2 = sp + nk;
+    const int ci = __popc(Cg & ((1u << lane) - 1u));
+    const int tgt = __shfl_sync(FULL_MASK, s.stk, (sp2 - 1 - ci) & 31);          // clones pop, ascending l
+    sp = sp2 - nc;
+    w.srcof[lane] = (unsigned char)lane;
+    __syncwarp();
+    if (clone) w.srcof[tgt] = (unsigned char)lane;
+    __syncwarp();
+    const int src_lane = w.srcof[lane];
+    __syncwarp();
+    const bool is_new = (src_lane != lane);
+    const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
+    const unsigned long long src_px = __shfl_sync(FULL_MASK, s.px, src_lane);
+    const unsigned long long src_ps = __shfl_sync(FULL_MASK, s.ps, src_lane);
+    const uint32_t src_sreg = __shfl_sync(FULL_MASK, s.sreg, src_lane);
+    if (is_new) {
+        s.active = true; s.pm = src_m1; u = 1u; s.px = src_px; s.ps = src_ps; s.sreg = src_sreg;
+    } else if (kill) {
+        s.active = false; s.pm = 0.0f;
+    } else if (s.active) {
+        u = keep0 ? 0u : 1u;
+        s.pm = keep0 ? m0 : m1;
+    }
+    return u;
+}
+
+// ---- partial sums after an odd bit (PolarCode.cpp:457-473) ----
+template <class C>
+__device__ __forceinline__ void update_partial_sums(const Warp& w, Lane& s, int phi, uint32_t u) {
+    constexpr int NLOG = C::NLOG;
+    const int t = __ffs(~phi) - 1;               // trailing ones, 1..NLOG
+    uint32_t P = u;
+    const int kmax = t < 5 ? t : 5;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        if (k < kmax) {
+            const uint32_t Sk = (s.sreg >> ((1 << k) - 1)) & ((1u << (1 << k)) - 1u);
+            P = (Sk ^ P) | (P << (1 << k));
+        }
+    }
+    if (t < 5) {
+        const int sh = (1 << t) - 1;
+        const uint32_t msk = ((1u << (1 << t)) - 1u) << sh;
+        s.sreg = (s.sreg & ~msk) | (P << sh);
+        return;
+    }
+    const int lam_end = NLOG - t;
+    int lam = NLOG - 5;
+    uint32_t* D = sbase_rt<C>(w, lam_end) + w.lane;
+    const int Wd = 1 << (t - 5);
+    D[(Wd - 1) * 32] = P;
+    for (; lam > lam_end; --lam) {
+        const int mw = 1 << (NLOG - lam - 5);
+        const int base = Wd - mw;
+        const uint32_t* S = sbase_rt<C>(w, lam) + get_ptr(s.ps, lam - 1);
+        for (int x = 0; x < mw; ++x) D[(base - mw + x) * 32] = S[x * 32] ^ D[(base + x) * 32];
+    }
+    if (lam_end >= 1) s.ps = set_ptr(s.ps, lam_end - 1, w.lane);
+}
+
+template <class C, int WPB, int BPS>
+__global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int N = C::N, NW = C::NW;
+    Warp w;
+    w.lane = threadIdx.x & 31;
+    const int lane = w.lane;
+    const int wib = threadIdx.x >> 5;
+    const int gwarp = blockIdx.x * WPB + wib;
+    const int total_warps = gridDim.x * WPB;
+    unsigned char* my = smem_raw + (size_t)C::SMEM_PER_WARP * wib;
+    w.sx = reinterpret_cast<float*>(my);
+    w.ss = reinterpret_cast<uint32_t*>(my + C::SX_ROWS * 128);
+    w.srcof = my + (C::SX_ROWS + C::SS_ROWS) * 128;
+    w.gx = a.gx + C::GX_FLOATS * gwarp;
+    w.xs = w.gx + (size_t)C::GX_ROWS * 32;
+    w.gs = a.gs + C::GS_WORDS * gwarp;
+    const int L = a.L, KW = (a.K + 31) >> 5;
+    const int c0 = L - 1;                          // first path popped from the free stack (PolarCode.cpp:250-263)
+
+    for (int cw = gwarp; cw < a.B; cw += total_warps) {
+        w.chan = a.llr + (size_t)cw * N;
+        Lane s;
+        s.active = (lane == c0);
+        s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0; s.stk = lane;
+        int sp = L - 1;
+        float lam_n = 0.0f;
+        uint32_t frozen_word = 0;
+
+#pragma unroll 1
+        for (int phi = 0; phi < N; ++phi) {
+            descend<C>(w, s, lam_n, phi, c0);
+            if ((phi & 31) == 0) frozen_word = a.frozen_words[phi >> 5];
+            uint32_t u = 0;
+            if ((frozen_word >> (phi & 31)) & 1u) {
+                if (s.active) s.pm += softplus_ref(-lam_n);          // PolarCode.cpp:475-487
+            } else {
+                u = info_step<C>(w, s, lam_n, L, sp);
+            }
+            if ((phi & 1) == 0) s.sreg = (s.sreg & ~1u) | u;
+            else update_partial_sums<C>(w, s, phi, u);
+            __syncwarp();
+        }
+
+        // ---- u-hat = packed polar transform of the re-encoded codeword (partial-sum layer 0) ----
+        uint32_t* D = sbase<C, 0>(w) + lane;
+        for (int sw = NW >> 1; sw >= 1; sw >>= 1)
+            for (int i = 0; i < NW; ++i)
+                if ((i & sw) == 0) D[i * 32] ^= D[(i + sw) * 32];
+        bool pass = true;
+        for (int i = 0; i < NW; ++i) {
+            uint32_t x = D[i * 32];
+            x ^= (x >> 16) & 0x0000FFFFu;
+            x ^= (x >> 8) & 0x00FF00FFu;
+            x ^= (x >> 4) & 0x0F0F0F0Fu;
+            x ^= (x >> 2) & 0x33333333u;
+            x ^= (x >> 1) & 0x55555555u;
+            D[i * 32] = x;
+        }
+        for (int r = 0; r < a.crc; ++r) {                 // PolarCode.cpp:93-108
+            uint32_t acc = 0;
+            for (int i = 0; i < NW; ++i) acc ^= D[i * 32] & a.crc_masks[r * NW + i];
+            if (__popc(acc) & 1) pass = false;
+        }
+        // ---- final pick, PolarCode.cpp:609-644 ----
+        const unsigned act = __ballot_sync(FULL_MASK, s.active);
+        const unsigned passm = __ballot_sync(FULL_MASK, s.active && pass);
+        const bool use_parity = (a.crc != 0) && (passm != 0);
+        const bool eligible = s.active && (use_parity ? pass : true) && (s.pm < CUDART_INF_F);
+        const unsigned best = __reduce_min_sync(FULL_MASK, eligible ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
+        const unsigned cand = __ballot_sync(FULL_MASK, eligible && __float_as_uint(s.pm) == best);
+        const int win = cand ? (__ffs(cand) - 1) : 0;
+        const bool win_active = (act >> win) & 1u;
+        __syncwarp();
+        const uint32_t* U = sbase<C, 0>(w) + win;
+        for (int t = lane; t < KW; t += 32) {               // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
+            uint32_t word = 0;
+            if (win_active) {
+                const int jmax = min(32, a.K - 32 * t);
+                for (int i = 0; i < jmax; ++i) {
+                    const int pos = a.info_order[32 * t + i];
+                    word |= ((U[(pos >> 5) * 32] >> (pos & 31)) & 1u) << i;
+                }
+            }
+            a.out[(size_t)cw * KW + t] = word;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace fast
