@@ -87,12 +87,11 @@ __device__ __forceinline__ float log1p_exp_neg(float x) {
 __device__ __forceinline__ float f_rule(float a, float b) {
     const float ma = fabsf(a), mb = fabsf(b);
     const float mn = fminf(ma, mb);
-    float r = __int_as_float(__float_as_int(mn) | ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
-    if (fmaxf(ma, mb) < 40.0f) {
-        const float s = fabsf(a + b), d = fabsf(a - b);
-        r += kLn2 * (lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d)));
-    }
-    return r;
+    const float r = __int_as_float(__float_as_int(mn) | ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
+    const float s = fabsf(a + b), d = fabsf(a - b);
+    // branch-free: the correction is always evaluated (4 MUFU) and dropped above the threshold
+    const float corr = kLn2 * (lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d)));
+    return r + ((fmaxf(ma, mb) < 40.0f) ? corr : 0.0f);
 }
 
 // log(1 + exp(x)) with the double-precision reference's corner behaviour
@@ -446,6 +445,8 @@ struct polar_b200_ctx {
     float* d_fgx = nullptr;                // scratch of the fast kernel
     uint32_t* d_fgs = nullptr;
     int fast_variant = -1, fast_warps = 0;
+    size_t l2_window = 0;
+    float l2_ratio = 1.0f;
     long long launches = 0;
     int last_wpb = 0, last_blocks = 0, last_smem = 0, last_kernel = 0;
     size_t scratch_bytes = 0;
@@ -526,13 +527,18 @@ struct FastVariant {
     int nlog, T, lamS, wpb, bps;
     size_t gx_floats, gs_words;
     int smem_per_warp;
-    void (*launch)(const fast::Args&, int blocks, cudaStream_t st);
+    cudaError_t (*launch)(const fast::Args&, int blocks, cudaStream_t st, const cudaLaunchAttribute* attrs, int nattrs);
     cudaError_t (*prepare)();
 };
 
 template <class C, int WPB, int BPS>
-void launch_fast(const fast::Args& a, int blocks, cudaStream_t st) {
-    fast::scl_fast_kernel<C, WPB, BPS><<<blocks, WPB * 32, C::SMEM_PER_WARP * WPB, st>>>(a);
+cudaError_t launch_fast(const fast::Args& a, int blocks, cudaStream_t st, const cudaLaunchAttribute* attrs, int nattrs) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(WPB * 32);
+    cfg.dynamicSmemBytes = C::SMEM_PER_WARP * WPB; cfg.stream = st;
+    cfg.attrs = const_cast<cudaLaunchAttribute*>(attrs); cfg.numAttrs = nattrs;
+    return cudaLaunchKernelEx(&cfg, fast::scl_fast_kernel<C, WPB, BPS>, a);
 }
 template <class C, int WPB, int BPS>
 cudaError_t prepare_fast() {
@@ -544,7 +550,7 @@ cudaError_t prepare_fast() {
       fast::Cfg<NLOG, T, LAMS>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS>,           \
       prepare_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS> }
 
-// first match for a given n is the default; POLAR_B200_FAST_VARIANT=<index> overrides
+// pick_fast_variant() chooses the default per block length; POLAR_B200_FAST_VARIANT=<index> overrides
 const FastVariant kFastVariants[] = {
     POLAR_FAST(11, 3, 5, 4, 3),    // 0: N=2048, layers 3-4 in HBM scratch, 12 warps/SM
     POLAR_FAST(11, 3, 6, 4, 5),    // 1: N=2048, layers 3-5 in HBM scratch, 20 warps/SM
@@ -553,6 +559,12 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST(10, 3, 4, 4, 3),    // 4: N=1024
     POLAR_FAST(12, 3, 6, 4, 3),    // 5: N=4096
     POLAR_FAST(8, 3, 3, 4, 4),     // 6: N=256
+    POLAR_FAST(11, 4, 6, 4, 4),    // 7: N=2048, top 4 layers virtual, layers 4-5 in HBM scratch, 16 warps/SM
+    POLAR_FAST(11, 4, 5, 4, 3),    // 8: N=2048, top 4 layers virtual, layer 4 in HBM scratch, 12 warps/SM
+    POLAR_FAST(11, 3, 6, 4, 4),    // 9: as 1 with 16 warps/SM (128 registers)
+    POLAR_FAST(11, 3, 6, 4, 6),    // 10: as 1 with 24 warps/SM (80 registers)
+    POLAR_FAST(11, 3, 7, 4, 6),    // 11: layers 3-6 in HBM scratch, 24 warps/SM
+    POLAR_FAST(11, 3, 7, 4, 8),    // 12: layers 3-6 in HBM scratch, 32 warps/SM (64 registers)
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
@@ -561,6 +573,9 @@ int pick_fast_variant(int n, int L) {
     if (L <= env_int("POLAR_B200_FAST_MIN_L", 16)) return -1;   // smaller lists: several codewords per warp (generic kernel)
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
     if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n) return forced;
+    // measured best per block length (profiles/): N=2048 -> variant 1, N=512 -> variant 3
+    const int preferred = (n == 11) ? 1 : (n == 9) ? 3 : -1;
+    if (preferred >= 0) return preferred;
     for (int i = 0; i < kNumFastVariants; ++i)
         if (kFastVariants[i].nlog == n) return i;
     return -1;
@@ -579,13 +594,42 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
         CU_TRY(v.prepare());
         c->fast_variant = variant; c->fast_warps = warps;
         c->scratch_bytes = (v.gx_floats * sizeof(float) + v.gs_words * sizeof(uint32_t)) * warps;
+        // optional: pin the per-warp LLR scratch in L2 with an access-policy window. Measured on
+        // B200 (profiles/): no gain over the default LRU behaviour (-1..-4%), so it is off by default.
+        c->l2_window = 0;
+        if (env_int("POLAR_B200_L2_PERSIST", 0)) {
+            int max_persist = 0, max_window = 0;
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+            cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+            size_t want = v.gx_floats * warps * sizeof(float);
+            if (max_persist > 0 && max_window > 0) {
+                size_t lim = want < (size_t)max_persist ? want : (size_t)max_persist;
+                if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, lim) == cudaSuccess) {
+                    c->l2_window = want < (size_t)max_window ? want : (size_t)max_window;
+                    c->l2_ratio = (float)((double)lim / (double)c->l2_window);
+                    if (c->l2_ratio > 1.0f) c->l2_ratio = 1.0f;
+                }
+            }
+            cudaGetLastError();
+        }
     }
     fast::Args a;
     a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = c->d_fgx; a.gs = c->d_fgs; a.B = B; a.K = c->K; a.crc = c->crc; a.L = L;
     const int need = (B + v.wpb - 1) / v.wpb;
     if (blocks > need) blocks = need;
-    v.launch(a, blocks, st);
+    cudaLaunchAttribute attr[1];
+    int nattr = 0;
+    if (c->l2_window) {
+        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[0].val.accessPolicyWindow.base_ptr = c->d_fgx;
+        attr[0].val.accessPolicyWindow.num_bytes = c->l2_window;
+        attr[0].val.accessPolicyWindow.hitRatio = c->l2_ratio;
+        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        nattr = 1;
+    }
+    CU_TRY(v.launch(a, blocks, st, attr, nattr));
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     c->last_wpb = v.wpb; c->last_blocks = blocks; c->last_smem = v.smem_per_warp * v.wpb; c->last_kernel = 1 + variant;

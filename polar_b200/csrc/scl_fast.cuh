@@ -140,7 +140,7 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s, float& lam_n)
             for (int wd = 0; wd < M / 32; ++wd) {
                 uint32_t word = 0;
                 if constexpr (ISG) word = sw[wd * 32];
-#pragma unroll 2
+#pragma unroll 1
                 for (int i0 = 0; i0 < 32; i0 += 4) {
                     float a[4], b[4];
 #pragma unroll
@@ -158,19 +158,23 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s, float& lam_n)
                 }
             }
         } else {
-            // small layers: fully unrolled, partial sums from the packed register
+            // small layers: partial sums from the packed register; chunks of <= 4 nodes
             constexpr int k = NLOG - LAM;                 // M = 2^k
+            constexpr int CH = M < 4 ? M : 4;
             const uint32_t field = s.sreg >> ((1 << k) - 1);
-            float a[M], b[M];
+#pragma unroll 1
+            for (int j0 = 0; j0 < M; j0 += CH) {
+                float a[CH], b[CH];
 #pragma unroll
-            for (int j = 0; j < M; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
+                for (int j = 0; j < CH; ++j) { a[j] = src[(j0 + j) * 32]; b[j] = src[(j0 + j + M) * 32]; }
 #pragma unroll
-            for (int j = 0; j < M; ++j) {
-                float y;
-                if constexpr (ISG) y = g_rule(a[j], b[j], (field >> j) & 1u);
-                else y = f_rule(a[j], b[j]);
-                if constexpr (LAM == NLOG) lam_n = y;
-                else (xbase<C, LAM>(w) + w.lane)[j * 32] = y;
+                for (int j = 0; j < CH; ++j) {
+                    float y;
+                    if constexpr (ISG) y = g_rule(a[j], b[j], (field >> (j0 + j)) & 1u);
+                    else y = f_rule(a[j], b[j]);
+                    if constexpr (LAM == NLOG) lam_n = y;
+                    else (xbase<C, LAM>(w) + w.lane)[(j0 + j) * 32] = y;
+                }
             }
         }
     }
@@ -199,7 +203,7 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                         sw[lev][i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
                 }
             }
-#pragma unroll 2
+#pragma unroll 1
             for (int bi = 0; bi < 32; ++bi) {
                 const int beta = wd * 32 + bi;
                 float v[CNT];
