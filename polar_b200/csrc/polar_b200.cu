@@ -552,19 +552,17 @@ cudaError_t prepare_fast() {
 
 // pick_fast_variant() chooses the default per block length; POLAR_B200_FAST_VARIANT=<index> overrides
 const FastVariant kFastVariants[] = {
-    POLAR_FAST(11, 3, 5, 4, 3),    // 0: N=2048, layers 3-4 in HBM scratch, 12 warps/SM
-    POLAR_FAST(11, 3, 6, 4, 5),    // 1: N=2048, layers 3-5 in HBM scratch, 20 warps/SM
-    POLAR_FAST(9, 3, 3, 4, 3),     // 2: N=512, everything per-path in shared memory, 12 warps/SM
+    POLAR_FAST(11, 3, 5, 4, 3),    // 0: N=2048, layers 3-4 in HBM scratch, 5-6 shared, 12 warps/SM
+    POLAR_FAST(11, 3, 6, 4, 5),    // 1: N=2048, layers 3-5 in HBM scratch, 6 shared, 20 warps/SM
+    POLAR_FAST(9, 3, 3, 4, 4),     // 2: N=512, layers 3-4 shared, 16 warps/SM
     POLAR_FAST(9, 3, 4, 4, 5),     // 3: N=512, layer 3 in HBM scratch, 20 warps/SM
-    POLAR_FAST(10, 3, 4, 4, 3),    // 4: N=1024
-    POLAR_FAST(12, 3, 6, 4, 3),    // 5: N=4096
+    POLAR_FAST(10, 3, 4, 4, 4),    // 4: N=1024
+    POLAR_FAST(12, 3, 6, 4, 4),    // 5: N=4096
     POLAR_FAST(8, 3, 3, 4, 4),     // 6: N=256
-    POLAR_FAST(11, 4, 6, 4, 4),    // 7: N=2048, top 4 layers virtual, layers 4-5 in HBM scratch, 16 warps/SM
-    POLAR_FAST(11, 4, 5, 4, 3),    // 8: N=2048, top 4 layers virtual, layer 4 in HBM scratch, 12 warps/SM
-    POLAR_FAST(11, 3, 6, 4, 4),    // 9: as 1 with 16 warps/SM (128 registers)
-    POLAR_FAST(11, 3, 6, 4, 6),    // 10: as 1 with 24 warps/SM (80 registers)
-    POLAR_FAST(11, 3, 7, 4, 6),    // 11: layers 3-6 in HBM scratch, 24 warps/SM
-    POLAR_FAST(11, 3, 7, 4, 8),    // 12: layers 3-6 in HBM scratch, 32 warps/SM (64 registers)
+    POLAR_FAST(11, 3, 5, 4, 4),    // 7: as 0 with 16 warps/SM (128 registers)
+    POLAR_FAST(11, 3, 6, 4, 4),    // 8: as 1 with 16 warps/SM
+    POLAR_FAST(11, 3, 5, 5, 3),    // 9: as 0 with 15 warps/SM (shared-memory limit)
+    POLAR_FAST(11, 4, 5, 4, 4),    // 10: top 4 layers virtual, layer 4 in HBM scratch, 16 warps/SM
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 

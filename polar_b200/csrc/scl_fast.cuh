@@ -14,7 +14,9 @@
 //     add, and the few f nodes that get evaluated twice add about 5% to the f count at T = 3.
 //     Per-path storage therefore starts at layer T: N/2^T rows instead of N;
 //   * layers T..LAMS-1 go to a per-warp scratch in HBM that is small enough to stay L2-resident,
-//     layers LAMS..NLOG-1 to shared memory, layer NLOG is a register;
+//     layers LAMS..NLOG-5 to shared memory; the four deepest layers (a 16-leaf subtree: 16 + 8 + 4
+//     + 2 LLRs per path) are registers, so the per-bit work at the bottom of the tree touches no
+//     memory at all and cloning a path there is a shuffle of those registers;
 //   * partial sums of the five deepest layers are one packed register per lane (cloning a path =
 //     one shuffle); the larger ones are packed words [word][lane] behind 5-bit column pointers;
 //   * the 2L -> L prune is "promote the best unlikely fork, demote the worst likely fork, until
@@ -31,12 +33,13 @@ struct Cfg {
     static constexpr int N = 1 << NLOG;
     static constexpr int MT = N >> T;                 // rows of the first per-path layer
     static constexpr int NW = N / 32;
+    static constexpr int LB = NLOG - 4;               // layer whose 16-entry array (and everything deeper) is registers
     static_assert(NLOG - T >= 5, "layer T must have at least 32 rows");
-    static_assert(LAMS >= T && LAMS <= NLOG, "bad shared-memory split");
+    static_assert(LAMS >= T && LAMS <= LB, "bad shared-memory split");
     // rows of per-path layers [a, b)
     static constexpr __host__ __device__ int rows(int a, int b) { return (N >> (a - 1)) - (N >> (b - 1)); }
     static constexpr int GX_ROWS = rows(T, LAMS);      // HBM scratch rows (32 floats each)
-    static constexpr int SX_ROWS = rows(LAMS, NLOG);   // shared rows
+    static constexpr int SX_ROWS = rows(LAMS, LB);     // shared rows (layers LAMS..NLOG-5)
     static constexpr int XS_FLOATS = N - MT;           // shared compact arrays XS_1..XS_T
     static constexpr __host__ __device__ int xs_off(int lev) { return N - (N >> (lev - 1)); }   // XS_lev at this float offset
     // partial-sum word layers: 1..NLOG-5 (>= 32 bits). Layers with >= 16 words live in HBM scratch.
@@ -125,60 +128,92 @@ __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
     return b + __int_as_float(__float_as_int(a) ^ (int)(bit << 31));
 }
 
-// ---- one per-path layer: X_LAM = f / g (X_{LAM-1}) ----
+// ---- one per-path layer in memory: X_LAM = f / g (X_{LAM-1}), T < LAM <= NLOG-5 ----
 template <class C, int LAM, bool ISG>
-__device__ __forceinline__ void layer_step(const Warp& w, Lane& s, float& lam_n) {
+__device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
     constexpr int M = C::N >> LAM;
-    constexpr int NLOG = C::NLOG;
+    static_assert(M >= 32, "memory layers have at least 32 rows");
     const float* src = xbase<C, LAM - 1>(w) + get_ptr(s.px, LAM - 1 - C::T);
     if (s.active) {
-        if constexpr (M >= 32) {
-            float* dst = xbase<C, LAM>(w) + w.lane;
-            const uint32_t* sw = nullptr;
-            if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
+        float* dst = xbase<C, LAM>(w) + w.lane;
+        const uint32_t* sw = nullptr;
+        if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
 #pragma unroll 1
-            for (int wd = 0; wd < M / 32; ++wd) {
-                uint32_t word = 0;
-                if constexpr (ISG) word = sw[wd * 32];
+        for (int wd = 0; wd < M / 32; ++wd) {
+            uint32_t word = 0;
+            if constexpr (ISG) word = sw[wd * 32];
 #pragma unroll 1
-                for (int i0 = 0; i0 < 32; i0 += 4) {
-                    float a[4], b[4];
+            for (int i0 = 0; i0 < 32; i0 += 4) {
+                float a[4], b[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        a[j] = src[(wd * 32 + i0 + j) * 32];
-                        b[j] = src[(wd * 32 + i0 + j + M) * 32];
-                    }
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float y;
-                        if constexpr (ISG) y = g_rule(a[j], b[j], (word >> (i0 + j)) & 1u);
-                        else y = f_rule(a[j], b[j]);
-                        dst[(wd * 32 + i0 + j) * 32] = y;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    a[j] = src[(wd * 32 + i0 + j) * 32];
+                    b[j] = src[(wd * 32 + i0 + j + M) * 32];
                 }
-            }
-        } else {
-            // small layers: partial sums from the packed register; chunks of <= 4 nodes
-            constexpr int k = NLOG - LAM;                 // M = 2^k
-            constexpr int CH = M < 4 ? M : 4;
-            const uint32_t field = s.sreg >> ((1 << k) - 1);
-#pragma unroll 1
-            for (int j0 = 0; j0 < M; j0 += CH) {
-                float a[CH], b[CH];
 #pragma unroll
-                for (int j = 0; j < CH; ++j) { a[j] = src[(j0 + j) * 32]; b[j] = src[(j0 + j + M) * 32]; }
-#pragma unroll
-                for (int j = 0; j < CH; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     float y;
-                    if constexpr (ISG) y = g_rule(a[j], b[j], (field >> (j0 + j)) & 1u);
+                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> (i0 + j)) & 1u);
                     else y = f_rule(a[j], b[j]);
-                    if constexpr (LAM == NLOG) lam_n = y;
-                    else (xbase<C, LAM>(w) + w.lane)[(j0 + j) * 32] = y;
+                    dst[(wd * 32 + i0 + j) * 32] = y;
                 }
             }
         }
     }
-    if constexpr (LAM < NLOG) s.px = set_ptr(s.px, LAM - C::T, w.lane);
+    s.px = set_ptr(s.px, LAM - C::T, w.lane);
+}
+
+// ---- the register subtree: layers NLOG-4 .. NLOG of one path ----
+struct Sub {
+    float x4[16], x3[8], x2[4], x1[2];
+};
+template <int K> __device__ __forceinline__ float* sub_arr(Sub& r) {
+    if constexpr (K == 4) return r.x4;
+    else if constexpr (K == 3) return r.x3;
+    else if constexpr (K == 2) return r.x2;
+    else return r.x1;
+}
+
+// layer NLOG-4 (16 entries) straight into registers from the 32-row layer above it
+template <class C, bool ISG>
+__device__ __forceinline__ void layer_to_regs(const Warp& w, const Lane& s, Sub& r) {
+    constexpr int LAM = C::LB;
+    const float* src = xbase<C, LAM - 1>(w) + get_ptr(s.px, LAM - 1 - C::T);
+    const uint32_t field = s.sreg >> 15;                  // packed partial sums of layer NLOG-4
+    if (s.active) {
+#pragma unroll
+        for (int j0 = 0; j0 < 16; j0 += 4) {
+            float a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = src[(j0 + j) * 32]; b[j] = src[(j0 + j + 16) * 32]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (ISG) r.x4[j0 + j] = g_rule(a[j], b[j], (field >> (j0 + j)) & 1u);
+                else r.x4[j0 + j] = f_rule(a[j], b[j]);
+            }
+        }
+    }
+}
+
+// level K of the subtree (2^K entries) from level K+1; K = 0 yields the decision LLR
+template <int K>
+__device__ __forceinline__ void sub_step(Sub& r, uint32_t sreg, bool isg, float& lam_n) {
+    constexpr int M = 1 << K;
+    const float* in = sub_arr<K + 1>(r);
+    const uint32_t field = sreg >> (M - 1);
+    if (isg) {
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const float y = g_rule(in[i], in[i + M], (field >> i) & 1u);
+            if constexpr (K == 0) lam_n = y; else sub_arr<K>(r)[i] = y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < M; ++i) {
+            const float y = f_rule(in[i], in[i + M]);
+            if constexpr (K == 0) lam_n = y; else sub_arr<K>(r)[i] = y;
+        }
+    }
 }
 
 // ---- layer T node NODE (1 .. 2^T - 1) for every path, from the channel / shared arrays ----
@@ -260,19 +295,15 @@ __device__ __forceinline__ void top_solo(const Warp& w, Lane& s, int c0) {
     s.px = set_ptr(s.px, 0, c0);
 }
 
-template <class C, int LAM>
-__device__ __forceinline__ void f_chain(const Warp& w, Lane& s, float& lam_n) {
-    layer_step<C, LAM, false>(w, s, lam_n);
-    if constexpr (LAM < C::NLOG) f_chain<C, LAM + 1>(w, s, lam_n);
-}
-
+// refresh everything above the register subtree for the 16-leaf block starting at phi0, ending with
+// the 16 LLRs of layer NLOG-4 in registers (PolarCode.cpp:422-455 for the layers involved)
 template <class C>
-__device__ __forceinline__ void descend(const Warp& w, Lane& s, float& lam_n, int phi, int c0) {
-    constexpr int T = C::T, NLOG = C::NLOG;
-    const int lam_top = (phi == 0) ? 0 : NLOG - (__ffs(phi) - 1);
+__device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, int phi0, int c0) {
+    constexpr int T = C::T, NLOG = C::NLOG, LB = C::LB;
+    const int lam_top = (phi0 == 0) ? 0 : NLOG - (__ffs(phi0) - 1);      // <= LB
     bool first = true;
     if (lam_top <= T) {
-        const int node = phi >> (NLOG - T);
+        const int node = phi0 >> (NLOG - T);
         switch (node) {
             case 0: top_solo<C>(w, s, c0); break;
 #define POLAR_TN(N_) case N_: if constexpr (N_ < (1 << T)) top_node<C, N_>(w, s); break;
@@ -287,23 +318,25 @@ __device__ __forceinline__ void descend(const Warp& w, Lane& s, float& lam_n, in
     switch (entry) {
 #define POLAR_LS(L_)                                                                           \
     case L_:                                                                                   \
-        if constexpr (L_ > T && L_ <= NLOG) {                                                  \
-            if (first) layer_step<C, L_, true>(w, s, lam_n);                                   \
-            else layer_step<C, L_, false>(w, s, lam_n);                                        \
+        if constexpr (L_ > T && L_ < LB) {                                                     \
+            if (first) layer_step<C, L_, true>(w, s);                                          \
+            else layer_step<C, L_, false>(w, s);                                               \
             first = false;                                                                     \
         }                                                                                      \
         [[fallthrough]];
         POLAR_LS(2) POLAR_LS(3) POLAR_LS(4) POLAR_LS(5) POLAR_LS(6) POLAR_LS(7) POLAR_LS(8) POLAR_LS(9)
-        POLAR_LS(10) POLAR_LS(11) POLAR_LS(12) POLAR_LS(13)
 #undef POLAR_LS
         default: break;
     }
+    if (first) layer_to_regs<C, true>(w, s, r);
+    else layer_to_regs<C, false>(w, s, r);
 }
 
 // ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607), 32 lanes = one codeword ----
 // Returns the decided bit of this lane's (possibly new) path.
 template <class C>
-__device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp) {
+__device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp, bool& permuted,
+                                              int& src_lane) {
     const int lane = w.lane;
     const float m0 = s.pm + softplus_ref(-lam_n);
     const float m1 = s.pm + softplus_ref(lam_n);
@@ -344,10 +377,13 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     const unsigned Kg = __ballot_sync(FULL_MASK, kill);
     const unsigned Cg = __ballot_sync(FULL_MASK, clone);
     uint32_t u = 0;
+    permuted = false;
+    src_lane = lane;
     if ((Kg | Cg) == 0) {
         if (s.active) { u = keep1 ? 1u : 0u; s.pm = keep1 ? m1 : m0; }
         return u;
     }
+    permuted = true;
     const int nk = __popc(Kg), nc = __popc(Cg);
     if (lane >= sp && lane < sp + nk) s.stk = (int)__fns(Kg, 0, lane - sp + 1);   // kills pushed ascending
     const int sp2 = sp + nk;
@@ -358,7 +394,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     __syncwarp();
     if (clone) w.srcof[tgt] = (unsigned char)lane;
     __syncwarp();
-    const int src_lane = w.srcof[lane];
+    src_lane = w.srcof[lane];
     __syncwarp();
     const bool is_new = (src_lane != lane);
     const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
@@ -437,22 +473,53 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0; s.stk = lane;
         int sp = L - 1;
         float lam_n = 0.0f;
-        uint32_t frozen_word = 0;
+        Sub r;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r.x4[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.x3[i] = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) r.x2[i] = 0.0f;
+        r.x1[0] = r.x1[1] = 0.0f;
 
 #pragma unroll 1
-        for (int phi = 0; phi < N; ++phi) {
-            descend<C>(w, s, lam_n, phi, c0);
-            if ((phi & 31) == 0) frozen_word = a.frozen_words[phi >> 5];
-            uint32_t u = 0;
-            if ((frozen_word >> (phi & 31)) & 1u) {
-                if (s.active) s.pm += softplus_ref(-lam_n);          // PolarCode.cpp:475-487
-            } else {
-                u = info_step<C>(w, s, lam_n, L, sp);
+        for (int phi0 = 0; phi0 < N; phi0 += 16) {
+            descend_block<C>(w, s, r, phi0, c0);
+            const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
+#pragma unroll 1
+            for (int j = 0; j < 16; ++j) {
+                // levels 3..0 of the register subtree: g at level ctz(j), f below it (all f for j = 0)
+                const int e = j ? (__ffs(j) - 1) : 3;
+                bool fg = (j != 0);
+                switch (e) {
+                    case 3: sub_step<3>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
+                    case 2: sub_step<2>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
+                    case 1: sub_step<1>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
+                    default: sub_step<0>(r, s.sreg, fg, lam_n);
+                }
+                uint32_t u = 0;
+                if ((frozen16 >> j) & 1u) {
+                    if (s.active) s.pm += softplus_ref(-lam_n);          // PolarCode.cpp:475-487
+                } else {
+                    bool permuted; int src_lane;
+                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane);
+                    if (permuted) {
+                        // a cloned path takes over its parent's live subtree registers
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) r.x4[i] = __shfl_sync(FULL_MASK, r.x4[i], src_lane);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) r.x3[i] = __shfl_sync(FULL_MASK, r.x3[i], src_lane);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) r.x2[i] = __shfl_sync(FULL_MASK, r.x2[i], src_lane);
+                        r.x1[0] = __shfl_sync(FULL_MASK, r.x1[0], src_lane);
+                        r.x1[1] = __shfl_sync(FULL_MASK, r.x1[1], src_lane);
+                    }
+                }
+                if ((j & 1) == 0) s.sreg = (s.sreg & ~1u) | u;
+                else update_partial_sums<C>(w, s, phi0 + j, u);
             }
-            if ((phi & 1) == 0) s.sreg = (s.sreg & ~1u) | u;
-            else update_partial_sums<C>(w, s, phi, u);
-            __syncwarp();
         }
+        __syncwarp();
 
         // ---- u-hat = packed polar transform of the re-encoded codeword (partial-sum layer 0) ----
         uint32_t* D = sbase<C, 0>(w) + lane;
