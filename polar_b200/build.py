@@ -39,7 +39,8 @@ def _stale(target, sources):
 
 def build(force=False, verbose=False):
     os.makedirs(LIB, exist_ok=True)
-    hdrs = [os.path.join(INC, "polar_b200.h"), os.path.join(CSRC, "PolarCode.h")]
+    hdrs = [os.path.join(INC, "polar_b200.h")] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+                                                   if f.endswith((".h", ".cuh"))]
     dev_so = os.path.join(LIB, "libpolar_b200.so")
     dev_src = [os.path.join(CSRC, "polar_b200.cu")]
     if force or _stale(dev_so, dev_src + hdrs):

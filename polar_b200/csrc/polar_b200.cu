@@ -89,9 +89,10 @@ __device__ __forceinline__ float f_rule(float a, float b) {
     const float mn = fminf(ma, mb);
     const float r = __int_as_float(__float_as_int(mn) | ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
     const float s = fabsf(a + b), d = fabsf(a - b);
-    // branch-free: the correction is always evaluated (4 MUFU) and dropped above the threshold
-    const float corr = kLn2 * (lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d)));
-    return r + ((fmaxf(ma, mb) < 40.0f) ? corr : 0.0f);
+    // branch-free: the correction is always evaluated (4 MUFU) and scaled by 0 above the threshold
+    const float diff = lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d));
+    const float scale = (fmaxf(ma, mb) < 40.0f) ? kLn2 : 0.0f;
+    return fmaf(diff, scale, r);
 }
 
 // log(1 + exp(x)) with the double-precision reference's corner behaviour
@@ -563,6 +564,10 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST(11, 3, 6, 4, 4),    // 8: as 1 with 16 warps/SM
     POLAR_FAST(11, 3, 5, 5, 3),    // 9: as 0 with 15 warps/SM (shared-memory limit)
     POLAR_FAST(11, 4, 5, 4, 4),    // 10: top 4 layers virtual, layer 4 in HBM scratch, 16 warps/SM
+    POLAR_FAST(11, 4, 6, 4, 5),    // 11: top 4 layers virtual, layers 4-5 in HBM scratch, 20 warps/SM
+    POLAR_FAST(11, 4, 5, 5, 3),    // 12: top 4 layers virtual, layer 4 in HBM scratch, 15 warps/SM
+    POLAR_FAST(11, 3, 6, 3, 6),    // 13: as 1 with 18 warps/SM (112 registers)
+    POLAR_FAST(11, 3, 5, 3, 5),    // 14: as 0 with 15 warps/SM (136 registers)
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 

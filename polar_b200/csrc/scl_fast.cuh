@@ -24,6 +24,7 @@
 //     its first round is the common no-fork-survives exit. It yields exactly the reference's
 //     sort / threshold / index-order selection (PolarCode.cpp:528-553).
 #pragma once
+#include <type_traits>
 
 namespace fast {
 
@@ -56,7 +57,7 @@ struct Cfg {
     static constexpr __host__ __device__ int ss_rows() { int r = 0; for (int j = 1; j <= SWL; ++j) if (!s_global(j)) r += swords(j); return r; }
     static constexpr int GS_ROWS = gs_rows();
     static constexpr int SS_ROWS = ss_rows();
-    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 32;
+    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64;
     static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + XS_FLOATS;
     static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
 };
@@ -75,7 +76,8 @@ struct Args {
 struct Warp {          // per-warp pointers
     float* sx;         // shared LLR rows
     uint32_t* ss;      // shared partial-sum rows
-    unsigned char* srcof;
+    unsigned char* srcof;   // clone scatter: srcof[new lane] = parent lane
+    unsigned char* stack;   // free-path stack (PolarCode.h:60 _inactivePathIndices)
     float* gx;         // HBM LLR rows, followed by XS
     float* xs;         // shared compact arrays
     uint32_t* gs;      // HBM partial-sum rows
@@ -89,7 +91,6 @@ struct Lane {          // per-path state
     unsigned long long px;   // column pointers of LLR layers T.. (index lam - T)
     unsigned long long ps;   // column pointers of partial-sum word layers 1..SWL (index lam - 1)
     uint32_t sreg;           // packed partial sums of layers NLOG-k, k = 0..4, at bit 2^k - 1
-    int stk;                 // free-path stack entry held by this lane
 };
 
 __device__ __forceinline__ unsigned brev_bits(unsigned x, int bits) { return bits ? (__brev(x) >> (32 - bits)) : 0u; }
@@ -138,26 +139,28 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
         float* dst = xbase<C, LAM>(w) + w.lane;
         const uint32_t* sw = nullptr;
         if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
-#pragma unroll 1
-        for (int wd = 0; wd < M / 32; ++wd) {
-            uint32_t word = 0;
-            if constexpr (ISG) word = sw[wd * 32];
-#pragma unroll 1
-            for (int i0 = 0; i0 < 32; i0 += 4) {
-                float a[4], b[4];
+        // groups of 4 nodes; the loads of group i+1 are issued before group i is computed so that the
+        // L2 / HBM latency of the scratch rows overlaps the MUFU work
+        float a[4], b[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    a[j] = src[(wd * 32 + i0 + j) * 32];
-                    b[j] = src[(wd * 32 + i0 + j + M) * 32];
-                }
+        for (int j = 0; j < 4; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
+        uint32_t word = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < M; i0 += 4) {
+            if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+            float na[4], nb[4];
+            const int nx = (i0 + 4 < M) ? i0 + 4 : i0;          // last group re-reads itself (harmless)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y;
-                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> (i0 + j)) & 1u);
-                    else y = f_rule(a[j], b[j]);
-                    dst[(wd * 32 + i0 + j) * 32] = y;
-                }
+            for (int j = 0; j < 4; ++j) { na[j] = src[(nx + j) * 32]; nb[j] = src[(nx + j + M) * 32]; }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float y;
+                if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
+                else y = f_rule(a[j], b[j]);
+                dst[(i0 + j) * 32] = y;
             }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
         }
     }
     s.px = set_ptr(s.px, LAM - C::T, w.lane);
@@ -216,6 +219,15 @@ __device__ __forceinline__ void sub_step(Sub& r, uint32_t sreg, bool isg, float&
     }
 }
 
+// compile-time loop: f(integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+    if constexpr (B < E) {
+        f(std::integral_constant<int, B>{});
+        static_for<B + 1, E>(f);
+    }
+}
+
 // ---- layer T node NODE (1 .. 2^T - 1) for every path, from the channel / shared arrays ----
 template <class C, int NODE>
 __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
@@ -227,42 +239,52 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
 #pragma unroll 1
         for (int wd = 0; wd < MT / 32; ++wd) {
             // partial-sum words of this path for the g levels: level lev, local element i sits at
-            // position beta + MT * brev(i) of layer lev
-            uint32_t sw[T + 1][CNT / 2 > 0 ? CNT / 2 : 1];
-#pragma unroll
-            for (int lev = S0 + 1; lev <= T; ++lev) {
-                if ((NODE >> (T - lev)) & 1) {
-                    const uint32_t* base = sbase_rt<C>(w, lev) + get_ptr(s.ps, lev - 1);
-#pragma unroll
-                    for (int i = 0; i < (1 << (T - lev)); ++i)
-                        sw[lev][i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
+            // position beta + MT * brev(i) of layer lev; flat index (1 << (T - lev)) + i
+            uint32_t sw[1 << T];
+            static_for<S0 + 1, T + 1>([&](auto lev_c) {
+                constexpr int lev = decltype(lev_c)::value;
+                if constexpr ((NODE >> (T - lev)) & 1) {
+                    const uint32_t* base = sbase<C, lev>(w) + get_ptr(s.ps, lev - 1);
+                    static_for<0, (1 << (T - lev))>([&](auto i_c) {
+                        constexpr int i = decltype(i_c)::value;
+                        sw[(1 << (T - lev)) + i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
+                    });
                 }
-            }
+            });
+            auto load_inputs = [&](int beta, float (&v)[CNT]) {
+                if constexpr (S0 == 0) {
+                    const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(beta, NLOG - T));
+                    static_for<0, CNT / 4>([&](auto q_c) {
+                        constexpr int q = decltype(q_c)::value;
+                        const float4 t4 = __ldg(c4 + q);
+                        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
+                    });
+                } else {
+                    const float* xs = w.xs + C::xs_off(S0);
+                    static_for<0, CNT>([&](auto i_c) {
+                        constexpr int i = decltype(i_c)::value;
+                        v[i] = xs[beta + MT * (int)cbrev(i, T - S0)];
+                    });
+                }
+            };
+            float nv[CNT];
+            load_inputs(wd * 32, nv);
 #pragma unroll 1
             for (int bi = 0; bi < 32; ++bi) {
                 const int beta = wd * 32 + bi;
                 float v[CNT];
-                if constexpr (S0 == 0) {
-                    const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(beta, NLOG - T));
 #pragma unroll
-                    for (int q = 0; q < CNT / 4; ++q) {
-                        const float4 t4 = __ldg(c4 + q);
-                        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
-                    }
-                } else {
-                    const float* xs = w.xs + C::xs_off(S0);
-#pragma unroll
-                    for (int i = 0; i < CNT; ++i) v[i] = xs[beta + MT * (int)cbrev(i, T - S0)];
-                }
-#pragma unroll
-                for (int lev = S0 + 1; lev <= T; ++lev) {
-                    const bool isg = (NODE >> (T - lev)) & 1;
-#pragma unroll
-                    for (int i = 0; i < (1 << (T - lev)); ++i) {
-                        if (isg) v[i] = g_rule(v[2 * i], v[2 * i + 1], (sw[lev][i] >> bi) & 1u);
+                for (int i = 0; i < CNT; ++i) v[i] = nv[i];
+                load_inputs(wd * 32 + ((bi + 1) & 31), nv);        // next beta of this word (wraps harmlessly)
+                static_for<S0 + 1, T + 1>([&](auto lev_c) {
+                    constexpr int lev = decltype(lev_c)::value;
+                    constexpr bool isg = (NODE >> (T - lev)) & 1;
+                    static_for<0, (1 << (T - lev))>([&](auto i_c) {
+                        constexpr int i = decltype(i_c)::value;
+                        if constexpr (isg) v[i] = g_rule(v[2 * i], v[2 * i + 1], (sw[(1 << (T - lev)) + i] >> bi) & 1u);
                         else v[i] = f_rule(v[2 * i], v[2 * i + 1]);
-                    }
-                }
+                    });
+                });
                 dst[beta * 32] = v[0];
             }
         }
@@ -338,17 +360,32 @@ template <class C>
 __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp, bool& permuted,
                                               int& src_lane) {
     const int lane = w.lane;
-    const float m0 = s.pm + softplus_ref(-lam_n);
-    const float m1 = s.pm + softplus_ref(lam_n);
+    // both fork metrics from one log1p(exp(-|x|)) (softplus_ref(-|x|) and softplus_ref(+|x|))
+    const float ax = fabsf(lam_n);
+    const float t = log1p_exp_neg(ax);
+    const float mlo = s.pm + ((ax >= 36.7368f) ? 0.0f : t);                       // likely fork
+    const float mhi = s.pm + ((ax >= 709.78271484375f) ? CUDART_INF_F : ax + t);  // unlikely fork
+    const bool neg = lam_n < 0.0f;
+    const float m0 = neg ? mhi : mlo, m1 = neg ? mlo : mhi;
     const unsigned act = __ballot_sync(FULL_MASK, s.active);
     const int A = __popc(act);
+    permuted = false;
+    src_lane = lane;
     bool keep0 = s.active, keep1 = s.active;
     if (2 * A > L) {
-        // keep the L best forks under (metric asc, fork index asc)
+        // keep the L best forks under (metric asc, fork index asc). Metrics are >= 0: uint order = float order.
+        const unsigned klo = __float_as_uint(mlo), khi = __float_as_uint(mhi);
+        if (A == L) {
+            // common exit: every unlikely fork is strictly worse than every likely fork
+            const unsigned kb = __reduce_min_sync(FULL_MASK, s.active ? khi : 0xFFFFFFFFu);
+            const unsigned ka = __reduce_max_sync(FULL_MASK, s.active ? klo : 0u);
+            if (kb > ka) {
+                if (s.active) s.pm = mlo;
+                return (m1 < m0) ? 1u : 0u;
+            }
+        }
         const bool like1 = m1 < m0;                        // likely fork is bit 1
         const unsigned lk = __ballot_sync(FULL_MASK, like1);
-        const unsigned klo = __float_as_uint(like1 ? m1 : m0);   // metrics are >= 0: uint order = float order
-        const unsigned khi = __float_as_uint(like1 ? m0 : m1);
         unsigned keptA = act, keptB = 0;
         int count = A;
         while (true) {
@@ -377,25 +414,24 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     const unsigned Kg = __ballot_sync(FULL_MASK, kill);
     const unsigned Cg = __ballot_sync(FULL_MASK, clone);
     uint32_t u = 0;
-    permuted = false;
-    src_lane = lane;
     if ((Kg | Cg) == 0) {
         if (s.active) { u = keep1 ? 1u : 0u; s.pm = keep1 ? m1 : m0; }
         return u;
     }
     permuted = true;
     const int nk = __popc(Kg), nc = __popc(Cg);
-    if (lane >= sp && lane < sp + nk) s.stk = (int)__fns(Kg, 0, lane - sp + 1);   // kills pushed ascending
+    const unsigned lt = (1u << lane) - 1u;
+    if (kill) w.stack[sp + __popc(Kg & lt)] = (unsigned char)lane;      // kills pushed in ascending path order
     const int sp2 = sp + nk;
-    const int ci = __popc(Cg & ((1u << lane) - 1u));
-    const int tgt = __shfl_sync(FULL_MASK, s.stk, (sp2 - 1 - ci) & 31);          // clones pop, ascending l
-    sp = sp2 - nc;
     w.srcof[lane] = (unsigned char)lane;
     __syncwarp();
-    if (clone) w.srcof[tgt] = (unsigned char)lane;
+    if (clone) {                                                        // clones pop, for ascending l
+        const int tgt = w.stack[sp2 - 1 - __popc(Cg & lt)];
+        w.srcof[tgt] = (unsigned char)lane;
+    }
+    sp = sp2 - nc;
     __syncwarp();
     src_lane = w.srcof[lane];
-    __syncwarp();
     const bool is_new = (src_lane != lane);
     const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
     const unsigned long long src_px = __shfl_sync(FULL_MASK, s.px, src_lane);
@@ -460,6 +496,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     w.sx = reinterpret_cast<float*>(my);
     w.ss = reinterpret_cast<uint32_t*>(my + C::SX_ROWS * 128);
     w.srcof = my + (C::SX_ROWS + C::SS_ROWS) * 128;
+    w.stack = w.srcof + 32;
     w.gx = a.gx + C::GX_FLOATS * gwarp;
     w.xs = w.gx + (size_t)C::GX_ROWS * 32;
     w.gs = a.gs + C::GS_WORDS * gwarp;
@@ -470,7 +507,9 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         w.chan = a.llr + (size_t)cw * N;
         Lane s;
         s.active = (lane == c0);
-        s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0; s.stk = lane;
+        s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0;
+        w.stack[lane] = (unsigned char)lane;            // free stack 0..L-2 (entries >= sp are don't-care)
+        __syncwarp();
         int sp = L - 1;
         float lam_n = 0.0f;
         Sub r;
@@ -489,13 +528,15 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
                 // levels 3..0 of the register subtree: g at level ctz(j), f below it (all f for j = 0)
-                const int e = j ? (__ffs(j) - 1) : 3;
-                bool fg = (j != 0);
-                switch (e) {
-                    case 3: sub_step<3>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
-                    case 2: sub_step<2>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
-                    case 1: sub_step<1>(r, s.sreg, fg, lam_n); fg = false; [[fallthrough]];
-                    default: sub_step<0>(r, s.sreg, fg, lam_n);
+                if (j & 1) {
+                    sub_step<0>(r, s.sreg, true, lam_n);
+                } else {
+                    const int e = j ? (__ffs(j) - 1) : 3;
+                    bool fg = (j != 0);
+                    if (e >= 3) { sub_step<3>(r, s.sreg, fg, lam_n); fg = false; }
+                    if (e >= 2) { sub_step<2>(r, s.sreg, fg, lam_n); fg = false; }
+                    sub_step<1>(r, s.sreg, fg, lam_n);
+                    sub_step<0>(r, s.sreg, false, lam_n);
                 }
                 uint32_t u = 0;
                 if ((frozen16 >> j) & 1u) {
