@@ -432,6 +432,7 @@ struct polar_b200_ctx {
     int device = 0;
     int n = 0, N = 0, K = 0, crc = 0, max_list = 0, max_batch = 0;
     int sm_count = 0;
+    int first_info = 0;                    // first unfrozen decoding position
     int KW = 0, NW = 0;
     uint32_t* d_frozen = nullptr;
     uint16_t* d_order = nullptr;
@@ -576,8 +577,8 @@ int pick_fast_variant(int n, int L) {
     if (L <= env_int("POLAR_B200_FAST_MIN_L", 16)) return -1;   // smaller lists: several codewords per warp (generic kernel)
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
     if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n) return forced;
-    // measured best per block length (profiles/): N=2048 -> variant 1, N=512 -> variant 3
-    const int preferred = (n == 11) ? 1 : (n == 9) ? 3 : -1;
+    // measured best per block length (profiles/): N=2048 -> variant 7, N=512 -> variant 3
+    const int preferred = (n == 11) ? 7 : (n == 9) ? 3 : -1;
     if (preferred >= 0) return preferred;
     for (int i = 0; i < kNumFastVariants; ++i)
         if (kFastVariants[i].nlog == n) return i;
@@ -619,6 +620,14 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     fast::Args a;
     a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = c->d_fgx; a.gs = c->d_fgs; a.B = B; a.K = c->K; a.crc = c->crc; a.L = L;
+    {
+        // leading frozen leaves handled by the cooperative phase (whole 16-leaf blocks below layer T's first node)
+        const int mt = (1 << v.nlog) >> v.T;
+        int pa = (c->first_info / 16) * 16;
+        if (pa > mt - 16) pa = mt - 16;
+        if (pa < 0 || env_int("POLAR_B200_PHASE_A", 1) == 0) pa = 0;
+        a.PA = pa;
+    }
     const int need = (B + v.wpb - 1) / v.wpb;
     if (blocks > need) blocks = need;
     cudaLaunchAttribute attr[1];
@@ -694,6 +703,8 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
     if ((rc = (int)cudaSetDevice(device)) != 0) return fail(rc);
     if ((rc = (int)cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device)) != 0) return fail(rc);
 
+    c->first_info = N;
+    for (int i = N - 1; i >= 0; --i) if (!frozen_mask[i]) c->first_info = i;
     std::vector<uint32_t> fw(c->NW, 0);
     for (int i = 0; i < N; ++i) if (frozen_mask[i]) fw[i >> 5] |= 1u << (i & 31);
     // parity row r over decoding positions: ones at order[j] where M[r][j] = 1, plus the

@@ -58,7 +58,8 @@ struct Cfg {
     static constexpr int GS_ROWS = gs_rows();
     static constexpr int SS_ROWS = ss_rows();
     static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64;
-    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + XS_FLOATS;
+    static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
+    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + XS_FLOATS + PA_FLOATS;
     static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
 };
 
@@ -71,6 +72,7 @@ struct Args {
     float* gx;
     uint32_t* gs;
     int B, K, crc, L;
+    int PA;            // leading frozen leaves decoded cooperatively (multiple of 16, < N >> T)
 };
 
 struct Warp {          // per-warp pointers
@@ -124,6 +126,15 @@ __device__ __forceinline__ uint32_t* sbase_rt(const Warp& w, int lam) {
     return p;
 }
 
+template <class C>
+__device__ __forceinline__ float* xbase_rt(const Warp& w, int lam) {
+    float* p = nullptr;
+#define POLAR_XB(L_) if constexpr (L_ >= C::T && L_ < C::LB) { if (lam == L_) p = xbase<C, L_>(w); }
+    POLAR_XB(2) POLAR_XB(3) POLAR_XB(4) POLAR_XB(5) POLAR_XB(6) POLAR_XB(7) POLAR_XB(8) POLAR_XB(9)
+#undef POLAR_XB
+    return p;
+}
+
 __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
     // (1 - 2u) a + b, PolarCode.cpp:448-451
     return b + __int_as_float(__float_as_int(a) ^ (int)(bit << 31));
@@ -139,28 +150,47 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
         float* dst = xbase<C, LAM>(w) + w.lane;
         const uint32_t* sw = nullptr;
         if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
-        // groups of 4 nodes; the loads of group i+1 are issued before group i is computed so that the
-        // L2 / HBM latency of the scratch rows overlaps the MUFU work
-        float a[4], b[4];
+        if constexpr (LAM - 1 < C::LAMS) {
+            // source rows are in the HBM/L2 scratch: groups of 4 nodes, the loads of group i+1 are issued
+            // before group i is computed so that their latency overlaps the MUFU work
+            float a[4], b[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
-        uint32_t word = 0;
+            for (int j = 0; j < 4; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
+            uint32_t word = 0;
 #pragma unroll 1
-        for (int i0 = 0; i0 < M; i0 += 4) {
-            if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
-            float na[4], nb[4];
-            const int nx = (i0 + 4 < M) ? i0 + 4 : i0;          // last group re-reads itself (harmless)
+            for (int i0 = 0; i0 < M; i0 += 4) {
+                if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+                float na[4], nb[4];
+                const int nx = (i0 + 4 < M) ? i0 + 4 : i0;          // last group re-reads itself (harmless)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { na[j] = src[(nx + j) * 32]; nb[j] = src[(nx + j + M) * 32]; }
+                for (int j = 0; j < 4; ++j) { na[j] = src[(nx + j) * 32]; nb[j] = src[(nx + j + M) * 32]; }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float y;
-                if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
-                else y = f_rule(a[j], b[j]);
-                dst[(i0 + j) * 32] = y;
+                for (int j = 0; j < 4; ++j) {
+                    float y;
+                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
+                    else y = f_rule(a[j], b[j]);
+                    dst[(i0 + j) * 32] = y;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
             }
+        } else {
+            // source rows are in shared memory: plain groups of 4
+            uint32_t word = 0;
+#pragma unroll 1
+            for (int i0 = 0; i0 < M; i0 += 4) {
+                if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+                float a[4], b[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
+                for (int j = 0; j < 4; ++j) { a[j] = src[(i0 + j) * 32]; b[j] = src[(i0 + j + M) * 32]; }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float y;
+                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
+                    else y = f_rule(a[j], b[j]);
+                    dst[(i0 + j) * 32] = y;
+                }
+            }
         }
     }
     s.px = set_ptr(s.px, LAM - C::T, w.lane);
@@ -294,7 +324,7 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
 
 // ---- node 0 of layer T: one path exists, the warp works across beta; fills XS_1..XS_T ----
 template <class C>
-__device__ __forceinline__ void top_solo(const Warp& w, Lane& s, int c0) {
+__device__ __forceinline__ void top_solo(const Warp& w, int c0) {
     constexpr int T = C::T, N = C::N, NLOG = C::NLOG;
     float* xs1 = w.xs + C::xs_off(1);
     for (int k = w.lane; k < N / 2; k += 32) {
@@ -314,7 +344,71 @@ __device__ __forceinline__ void top_solo(const Warp& w, Lane& s, int c0) {
     float* col = xbase<C, T>(w) + c0;
     for (int b = w.lane; b < C::MT; b += 32) col[b * 32] = xt[b];
     __syncwarp();
-    s.px = set_ptr(s.px, 0, c0);
+}
+
+// ---- phase A: the leading PA leaves are frozen and only one path exists, so the warp decodes them
+// across beta instead of one lane doing all the work. All partial sums are zero there, which also
+// removes the bit-serial dependency: a completely frozen subtree is evaluated level by level
+// (f to the left half, a + b to the right half of every node), its leaf LLRs land in decoding order
+// and the path metric is accumulated in exactly the reference's order (PolarCode.cpp:475-487).
+// On return the lane-per-path state is what bit-serial decoding of leaves 0..PA-1 would have left:
+// layers T..NLOG-5 of the path to leaf PA in column c0, zero partial sums, x4 = layer NLOG-4.
+template <class C>
+__device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
+    constexpr int T = C::T, LB = C::LB, MT = C::MT, N = C::N;
+    const int lane = w.lane;
+    top_solo<C>(w, c0);
+    float* bufA = w.xs + C::XS_FLOATS;
+    float* bufB = bufA + MT / 2;
+    float* V = bufB + MT / 2;
+    const float* cur = w.xs + C::xs_off(T);
+    float pm = 0.0f;
+    int offset = 0;
+#pragma unroll 1
+    for (int lam = T; lam < LB; ++lam) {
+        const int half = (N >> lam) >> 1;
+        float* nxt = ((lam - T) & 1) ? bufB : bufA;
+        if (PA >= offset + half) {
+            // the left child's subtree [offset, offset + half) is completely frozen
+            for (int b = lane; b < half; b += 32) V[b] = f_rule(cur[b], cur[b + half]);
+            __syncwarp();
+#pragma unroll 1
+            for (int m = half; m >= 2; m >>= 1) {
+                const int hm = m >> 1;
+                for (int idx = lane; idx < half / 2; idx += 32) {
+                    const int p = (idx / hm) * m + (idx % hm);
+                    const float x = V[p], y = V[p + hm];
+                    V[p] = f_rule(x, y);
+                    V[p + hm] = y + x;                                   // g with u = 0
+                }
+                __syncwarp();
+            }
+            for (int b = lane; b < half; b += 32) V[b] = softplus_ref(-V[b]);
+            __syncwarp();
+#pragma unroll 4
+            for (int i = 0; i < half; ++i) pm += V[i];                   // leaf order, as the reference adds them
+            for (int b = lane; b < half; b += 32) nxt[b] = cur[b + half] + cur[b];
+            if (lam + 1 <= C::SWL) {                                     // its partial sums: all zero
+                uint32_t* sw = sbase_rt<C>(w, lam + 1) + c0;
+                for (int x = lane; x < C::swords(lam + 1); x += 32) sw[x * 32] = 0u;
+            }
+            offset += half;
+        } else {
+            for (int b = lane; b < half; b += 32) nxt[b] = f_rule(cur[b], cur[b + half]);
+        }
+        __syncwarp();
+        if (lam + 1 < LB) {
+            float* col = xbase_rt<C>(w, lam + 1) + c0;
+            for (int b = lane; b < half; b += 32) col[b * 32] = nxt[b];
+        }
+        cur = nxt;
+    }
+    __syncwarp();
+    const float keep = cur[lane & 15];
+    __syncwarp();
+    if (lane < 16) V[lane] = keep;                       // layer NLOG-4 of the path, picked up by the caller
+    __syncwarp();
+    return pm;
 }
 
 // refresh everything above the register subtree for the 16-leaf block starting at phi0, ending with
@@ -327,7 +421,7 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
     if (lam_top <= T) {
         const int node = phi0 >> (NLOG - T);
         switch (node) {
-            case 0: top_solo<C>(w, s, c0); break;
+            case 0: top_solo<C>(w, c0); s.px = set_ptr(s.px, 0, c0); break;
 #define POLAR_TN(N_) case N_: if constexpr (N_ < (1 << T)) top_node<C, N_>(w, s); break;
             POLAR_TN(1) POLAR_TN(2) POLAR_TN(3) POLAR_TN(4) POLAR_TN(5) POLAR_TN(6) POLAR_TN(7)
             POLAR_TN(8) POLAR_TN(9) POLAR_TN(10) POLAR_TN(11) POLAR_TN(12) POLAR_TN(13) POLAR_TN(14) POLAR_TN(15)
@@ -448,6 +542,29 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     return u;
 }
 
+// partial-sum chain above the register layers (runs after 1 bit in 32): out of line to keep the
+// per-bit code small
+template <class C>
+__device__ __noinline__ unsigned long long deep_chain(uint32_t* gs, uint32_t* ss, int lane, unsigned long long ps,
+                                                      uint32_t P, int t) {
+    constexpr int NLOG = C::NLOG;
+    Warp w;
+    w.gs = gs; w.ss = ss; w.lane = lane;
+    const int lam_end = NLOG - t;
+    int lam = NLOG - 5;
+    uint32_t* D = sbase_rt<C>(w, lam_end) + lane;
+    const int Wd = 1 << (t - 5);
+    D[(Wd - 1) * 32] = P;
+    for (; lam > lam_end; --lam) {
+        const int mw = 1 << (NLOG - lam - 5);
+        const int base = Wd - mw;
+        const uint32_t* S = sbase_rt<C>(w, lam) + get_ptr(ps, lam - 1);
+        for (int x = 0; x < mw; ++x) D[(base - mw + x) * 32] = S[x * 32] ^ D[(base + x) * 32];
+    }
+    if (lam_end >= 1) ps = set_ptr(ps, lam_end - 1, lane);
+    return ps;
+}
+
 // ---- partial sums after an odd bit (PolarCode.cpp:457-473) ----
 template <class C>
 __device__ __forceinline__ void update_partial_sums(const Warp& w, Lane& s, int phi, uint32_t u) {
@@ -468,18 +585,7 @@ __device__ __forceinline__ void update_partial_sums(const Warp& w, Lane& s, int 
         s.sreg = (s.sreg & ~msk) | (P << sh);
         return;
     }
-    const int lam_end = NLOG - t;
-    int lam = NLOG - 5;
-    uint32_t* D = sbase_rt<C>(w, lam_end) + w.lane;
-    const int Wd = 1 << (t - 5);
-    D[(Wd - 1) * 32] = P;
-    for (; lam > lam_end; --lam) {
-        const int mw = 1 << (NLOG - lam - 5);
-        const int base = Wd - mw;
-        const uint32_t* S = sbase_rt<C>(w, lam) + get_ptr(s.ps, lam - 1);
-        for (int x = 0; x < mw; ++x) D[(base - mw + x) * 32] = S[x * 32] ^ D[(base + x) * 32];
-    }
-    if (lam_end >= 1) s.ps = set_ptr(s.ps, lam_end - 1, w.lane);
+    s.ps = deep_chain<C>(w.gs, w.ss, w.lane, s.ps, P, t);
 }
 
 template <class C, int WPB, int BPS>
@@ -521,9 +627,20 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         for (int i = 0; i < 4; ++i) r.x2[i] = 0.0f;
         r.x1[0] = r.x1[1] = 0.0f;
 
+        bool have_x4 = false;
+        if (a.PA > 0) {
+            s.pm = phase_a<C>(w, a.PA, c0);              // out of line: runs once per codeword
+            const float* x4src = w.xs + C::XS_FLOATS + C::MT;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) r.x4[i] = x4src[i];
+            const unsigned long long rep = 0x0084210842108421ull * (unsigned long long)c0;   // c0 in every 5-bit field
+            s.px = rep; s.ps = rep; s.sreg = 0u;
+            have_x4 = true;
+        }
 #pragma unroll 1
-        for (int phi0 = 0; phi0 < N; phi0 += 16) {
-            descend_block<C>(w, s, r, phi0, c0);
+        for (int phi0 = a.PA; phi0 < N; phi0 += 16) {
+            if (!have_x4) descend_block<C>(w, s, r, phi0, c0);
+            have_x4 = false;
             const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
 #pragma unroll 1
             for (int j = 0; j < 16; ++j) {
