@@ -48,6 +48,16 @@ def workload_name(cfg, batch):
         idx, 1 << n, K, crc, L, "%.2f-%.2f sweep" % (sweep[0], sweep[-1]) if len(sweep) > 1 else "%.2f" % sweep[0], batch)
 
 
+def recorded_traffic(cfg, batch):
+    """DRAM bytes per launch from the committed ncu --set full capture (profiles/ncu_traffic.json,
+    written by tools/ncu_traffic.py), scaled from the captured batch to this one; None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[cfg]
+        return d["dram_bytes_per_codeword"] * batch, d
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -236,6 +246,7 @@ def run_ours(args):
         value = world * B * args.steps / (ms * 1e-3)
         bytes_cw = 4 * N + (K + 7) // 8
         peak, peak_src = measured_peak()
+        traffic, traffic_src = recorded_traffic(args.config, B)
         achieved = B * bytes_cw / (ms_step * 1e-3) / 1e9     # per GPU: one launch decodes this rank's B codewords
         out = {
             "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
@@ -245,10 +256,14 @@ def run_ours(args):
                        "l2": "input %d MiB per GPU per step > 126 MB L2, no flush needed" % (B * N * 4 >> 20),
                        "sharding": "contiguous codeword blocks per rank, no data-path collective; counters all-reduced"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "bytes_per_codeword": bytes_cw,
-                         "kernel": "scl_decode_kernel", "kernel_ms": ms_step},
+                         "traffic": traffic, "peak_source": peak_src, "bytes_per_codeword": bytes_cw,
+                         "algorithmic_bytes_per_launch": B * bytes_cw,
+                         "traffic_source": (traffic_src or {}).get("source"),
+                         "kernel": "scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel",
+                         "kernel_kind": code.info(6), "kernel_ms": ms_step},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "codewords/s", "h2d_bytes_per_step": B * N * 4,
-                    "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok},
+                    "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok,
+                    "pipelined_chunks": code.info(7)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "bler": float(counts[0, 0, 0] / counts[0, 0, 1]),

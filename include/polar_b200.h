@@ -93,9 +93,11 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* ctx, const float* llr, int B, int 
                               uint32_t* info_packed, void* cuda_stream);
 
 /*
- * Same, host memory in and out: H2D copy of llr, decode, D2H copy of the packed bits,
- * then a stream synchronise (the result is valid on return). This is the end-to-end
- * path the host class and bench.py's `e2e` leg use. B <= max_batch.
+ * Same, host memory in and out: H2D copy of llr, decode, D2H copy of the packed bits; the
+ * result is valid on return. The batch is cut into a few chunks whose transfers and decodes
+ * overlap on internal streams (pinned host memory makes the copies truly asynchronous);
+ * `cuda_stream` is only synchronised on entry. This is the end-to-end path the host class and
+ * bench.py's `e2e` leg use. B <= max_batch.
  */
 int polar_b200_decode_scl_llr_host(polar_b200_ctx* ctx, const float* llr_host, int B, int L,
                                    uint32_t* info_packed_host, void* cuda_stream);
@@ -117,7 +119,8 @@ enum {
     POLAR_B200_INFO_BLOCKS = 3,          /* grid size of the last decode launch             */
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
-    POLAR_B200_INFO_KERNEL_KIND = 6      /* last decode: 0 = generic kernel, 1 + i = fast variant i */
+    POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i */
+    POLAR_B200_INFO_HOST_CHUNKS = 7      /* chunks the last *_host call was pipelined in            */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
 

@@ -444,6 +444,11 @@ struct polar_b200_ctx {
     int scratch_lamS = -1;
     float* d_llr_stage = nullptr;
     uint32_t* d_out_stage = nullptr;
+    // host entry point: H2D / decode / D2H of consecutive chunks overlap on three internal streams
+    cudaStream_t st_h2d = nullptr, st_run = nullptr, st_d2h = nullptr;
+    static constexpr int kMaxChunks = 16;
+    cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
+    int last_chunks = 0;
     float* d_fgx = nullptr;                // scratch of the fast kernel
     uint32_t* d_fgs = nullptr;
     int fast_variant = -1, fast_warps = 0;
@@ -734,6 +739,10 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs);
+    if (c->st_h2d) {
+        cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_run); cudaStreamDestroy(c->st_d2h);
+        for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
+    }
     delete c;
     return POLAR_B200_OK;
 }
@@ -779,12 +788,54 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
     if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)cuda_stream;
-    CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, st));
-    int rc = polar_b200_decode_scl_llr(c, c->d_llr_stage, B, L, c->d_out_stage, cuda_stream);
-    if (rc) return rc;
-    CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));     // work queued by the caller comes first
+    if (!c->st_h2d) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_run, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) {
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    // Chunks are whole "rounds" of the persistent grid (every warp decodes the same number of
+    // codewords per chunk), so splitting costs no extra tail; about 6 chunks hide the PCIe time.
+    int per_round;
+    {
+        const int fv = pick_fast_variant(c->n, L);
+        if (fv >= 0) {
+            per_round = c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb;
+        } else {
+            LaunchPlan p = make_plan(c);
+            int W = 1; while (W < L) W <<= 1;
+            per_round = p.blocks * p.wpb * (32 / W);
+        }
+    }
+    // Chunks are whole rounds of the persistent grid (a chunk smaller than a round takes as long as
+    // a full one, the decode being latency-bound per warp), about 6 of them hide the PCIe time.
+    const int rounds = (B + per_round - 1) / per_round;
+    long long chunk = (long long)((rounds + 5) / 6) * per_round;
+    if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || chunk <= 0) chunk = B;
+    int nchunks = (int)((B + chunk - 1) / chunk);
+    if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
+    c->last_chunks = nchunks;
+    for (int i = 0; i < nchunks; ++i) {
+        const long long lo = (long long)i * chunk;
+        const int nb = (int)((lo + chunk <= B) ? chunk : (B - lo));
+        float* d_in = c->d_llr_stage + (size_t)lo * c->N;
+        uint32_t* d_o = c->d_out_stage + (size_t)lo * c->KW;
+        CU_TRY(cudaMemcpyAsync(d_in, llr_host + (size_t)lo * c->N, (size_t)nb * c->N * sizeof(float),
+                               cudaMemcpyHostToDevice, c->st_h2d));
+        CU_TRY(cudaEventRecord(c->ev_in[i], c->st_h2d));
+        CU_TRY(cudaStreamWaitEvent(c->st_run, c->ev_in[i], 0));
+        int rc = polar_b200_decode_scl_llr(c, d_in, nb, L, d_o, c->st_run);
+        if (rc) return rc;
+        CU_TRY(cudaEventRecord(c->ev_done[i], c->st_run));
+        CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_done[i], 0));
+        CU_TRY(cudaMemcpyAsync(info_packed_host + (size_t)lo * c->KW, d_o, (size_t)nb * c->KW * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->st_d2h));
+    }
+    CU_TRY(cudaStreamSynchronize(c->st_d2h));
     return POLAR_B200_OK;
 }
 
@@ -809,6 +860,7 @@ long long polar_b200_get_info(polar_b200_ctx* c, int key) {
         case POLAR_B200_INFO_SMEM_BYTES: return c->last_smem;
         case POLAR_B200_INFO_SCRATCH_BYTES: return (long long)c->scratch_bytes;
         case POLAR_B200_INFO_KERNEL_KIND: return c->last_kernel;
+        case POLAR_B200_INFO_HOST_CHUNKS: return c->last_chunks;
         default: return -1;
     }
 }

@@ -9,5 +9,5 @@ python bench.py --impl reference --steps 3 --warmup 3 > gpurun_out/bench_ref_$ta
 for c in c2 c3 c5; do python bench.py --config $c --steps 5 --warmup 3 --cpu-seconds 5 >> gpurun_out/bench_other_$tag.json 2>> gpurun_out/bench_$tag.err; done; cat gpurun_out/bench_other_$tag.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ncu_bench_$tag.log 2>&1
 tail -12 gpurun_out/launches_$tag.csv
-ncu --set full --clock-control none --import-source on -k regex:scl_decode -s 3 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 --batch 16384 > gpurun_out/ncu_full_$tag.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:scl_ -s 3 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 --batch 16384 > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out/
