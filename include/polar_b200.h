@@ -111,6 +111,22 @@ int polar_b200_count_errors(polar_b200_ctx* ctx, const uint32_t* info_packed,
                             const uint32_t* truth_packed, int B, uint8_t* block_err,
                             unsigned long long* n_err, void* cuda_stream);
 
+/*
+ * Synthetic front end on the device: B codewords with global indices first_index .. first_index+B-1.
+ * Replaces the per-run generation of the reference's BLER loop -- info bits and noise
+ * (PolarCode.cpp:703-710), encoder (:60-91, :712), BPSK/AWGN channel and LLR (:715, :744-753, N0 = 1) --
+ * with a counter-based generator (Philox4x32-10, key = seed, counter = (codeword index, draw)), so a
+ * codeword depends only on (seed, index), not on batching or on the number of GPUs. The reference's own
+ * RNG sequence (rand(), std::default_random_engine) is NOT reproduced here; the host class's
+ * get_bler_quick keeps doing that on the host.
+ *   ebno_db   host, [n_ebno] (n_ebno <= 64); codeword i uses ebno_db[i % n_ebno]
+ *   llr       device, [B][N] fp32 out;  truth_packed  device, [B][ceil(K/32)] out (the info bits)
+ * K <= 2048 and N <= 8192.
+ */
+int polar_b200_synthesize(polar_b200_ctx* ctx, unsigned long long seed, long long first_index, int B,
+                          const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed,
+                          void* cuda_stream);
+
 /* Introspection (all return -1 for an unknown key). */
 enum {
     POLAR_B200_INFO_KERNEL_LAUNCHES = 0, /* kernels this ctx has launched so far            */

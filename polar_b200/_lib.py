@@ -38,6 +38,7 @@ def dev():
         lib.polar_b200_decode_scl_llr.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_b200_decode_scl_llr_host.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_b200_count_errors.argtypes = [vp, vp, vp, ip, vp, vp, vp]
+        lib.polar_b200_synthesize.argtypes = [vp, C.c_ulonglong, C.c_longlong, ip, vp, ip, vp, vp, vp]
         lib.polar_b200_get_info.restype = C.c_longlong
         lib.polar_b200_get_info.argtypes = [vp, ip]
         _dev = lib

@@ -35,6 +35,29 @@ def sweep_counts(code, decode_fn, list_sizes, ebno_db, total, seed, rank=0, worl
     return counts
 
 
+def sweep_counts_device(code, list_sizes, ebno_db, total, seed, rank=0, world=1, chunk=65536):
+    """Same counters with everything on the GPU: codewords are synthesised on the device
+    (polar_b200_synthesize), decoded and compared there; only the counters come back.
+    `total` codewords PER Eb/N0 point, split over ranks; point ie uses seed + ie."""
+    import torch
+    counts = np.zeros((len(list_sizes), len(ebno_db), 2), np.int64)
+    lo = total * rank // world
+    hi = total * (rank + 1) // world
+    dev = torch.device("cuda", code.device)
+    nerr = torch.zeros(1, dtype=torch.int64, device=dev)
+    for ie, eb in enumerate(ebno_db):
+        for first in range(lo, hi, chunk):
+            nb = min(chunk, hi - first)
+            llr, truth = code.synthesize(nb, [eb], seed + ie, first_index=first)
+            for il, L in enumerate(list_sizes):
+                out = code.decode_device(llr, int(L))
+                nerr.zero_()
+                code.count_errors(out, truth, None, nerr)
+                counts[il, ie, 0] += int(nerr.item())
+                counts[il, ie, 1] += nb
+    return counts
+
+
 def all_reduce_counts(counts, device=None):
     """Sum the counters over ranks (no-op without an initialised process group)."""
     import torch

@@ -127,6 +127,24 @@ class PolarCode:
             ctx, dec.data_ptr(), truth.data_ptr(), B, block_err.data_ptr() if block_err is not None else None,
             n_err.data_ptr() if n_err is not None else None, C.c_void_p(stream)))
 
+    def synthesize(self, B, ebno_db, seed, first_index=0, llr=None, truth=None, stream=None, device=None):
+        """Device-side synthetic workload (include/polar_b200.h: polar_b200_synthesize): B codewords with
+        global indices first_index.., Eb/N0 of codeword i = ebno_db[i % len(ebno_db)].
+        Returns (llr [B][N] float32 cuda, truth [B][KW] int32 cuda = packed info bits)."""
+        import torch
+        dev = torch.device("cuda", self.device) if device is None else device
+        if llr is None:
+            llr = torch.empty((B, self.N), dtype=torch.float32, device=dev)
+        if truth is None:
+            truth = torch.empty((B, self.KW), dtype=torch.int32, device=dev)
+        if stream is None:
+            stream = torch.cuda.current_stream(dev).cuda_stream
+        eb = np.ascontiguousarray(np.atleast_1d(ebno_db), np.float64)
+        _lib.check(_lib.dev().polar_b200_synthesize(self.ctx(1), int(seed) & (2**64 - 1), int(first_index), int(B),
+                                                    eb.ctypes.data, len(eb), llr.data_ptr(), truth.data_ptr(),
+                                                    C.c_void_p(stream)))
+        return llr, truth
+
     def ctx(self, min_batch=1):
         c = _lib.host().polar_host_ctx(self._h, int(min_batch))
         if not c:

@@ -31,6 +31,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <math.h>
 
 #include <new>
 #include <vector>
@@ -420,6 +421,133 @@ __global__ void count_errors_kernel(const uint32_t* dec, const uint32_t* truth, 
     if (n_err && (threadIdx.x & 31) == 0 && m) atomicAdd(n_err, (unsigned long long)__popc(m));
 }
 
+// ---- synthetic front end: info bits -> reference encoder -> BPSK/AWGN -> fp32 LLRs, one warp per codeword ----
+// Replaces the per-run generation of the reference's BLER loop (PolarCode.cpp:703-716 info bits + noise,
+// :60-91 encoder, :744-753 channel and LLR) with a counter-based generator: Philox4x32-10 keyed by the seed,
+// counter = (global codeword index, draw index), so a codeword depends only on (seed, index).
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
+                                              uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+struct SynthArgs {
+    float* llr;                     // [B][N]
+    uint32_t* truth;                // [B][KW]
+    const uint16_t* inv_order;      // [N]: info index j (< K), K + r for parity bit r, 0xFFFF for frozen positions
+    const uint32_t* crc_rows;       // [crc][KW]: parity matrix rows packed over the info index
+    const float* amp;               // [n_ebno]: a = 10^(EbN0/20) sqrt(K/N)   (PolarCode.cpp:744-745)
+    unsigned long long seed;
+    long long first_index;
+    int B, n, K, crc, n_ebno;
+};
+
+__global__ void __launch_bounds__(128) synth_kernel(const SynthArgs a) {
+    __shared__ uint32_t sm_info[4][64];      // K <= 2048 info bits per warp
+    __shared__ uint32_t sm_u[4][256];        // N <= 8192 bits per warp
+    __shared__ uint32_t sm_crc[4];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int N = 1 << a.n, NW = (N + 31) >> 5, KW = (a.K + 31) >> 5;
+    uint32_t* info = sm_info[wib];
+    uint32_t* u = sm_u[wib];
+    const uint32_t k0 = (uint32_t)a.seed, k1 = (uint32_t)(a.seed >> 32);
+    for (int b = blockIdx.x * 4 + wib; b < a.B; b += gridDim.x * 4) {
+        const unsigned long long gidx = (unsigned long long)(a.first_index + b);
+        const uint32_t g0 = (uint32_t)gidx, g1 = (uint32_t)(gidx >> 32);
+        // info bits: draw index space 0 (counter word 3 = 0)
+        for (int w4 = lane; w4 * 4 < KW; w4 += 32) {
+            uint32_t r[4];
+            philox4x32_10(g0, g1, (uint32_t)w4, 0u, k0, k1, r);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int w = w4 * 4 + q;
+                if (w < KW) {
+                    uint32_t x = r[q];
+                    if (32 * w + 32 > a.K) x &= (1u << (a.K - 32 * w)) - 1u;      // last partial word
+                    info[w] = x;
+                    a.truth[(size_t)b * KW + w] = x;
+                }
+            }
+        }
+        __syncwarp();
+        // parity ("CRC") bits, PolarCode.cpp:68-74
+        if (lane == 0) sm_crc[wib] = 0;
+        __syncwarp();
+        for (int r = 0; r < a.crc; ++r) {
+            uint32_t acc = 0;
+            for (int w = lane; w < KW; w += 32) acc ^= info[w] & a.crc_rows[(size_t)r * KW + w];
+            acc = __reduce_xor_sync(FULL_MASK, acc);
+            if (lane == 0 && (__popc(acc) & 1)) sm_crc[wib] |= 1u << r;
+        }
+        __syncwarp();
+        const uint32_t crcbits = sm_crc[wib];
+        // u vector in decoding order, PolarCode.cpp:65-74
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t word = 0;
+            const int nb = (N - 32 * w) < 32 ? (N - 32 * w) : 32;
+            for (int i = 0; i < nb; ++i) {
+                const unsigned j = a.inv_order[32 * w + i];
+                uint32_t bit = 0;
+                if (j < (unsigned)a.K) bit = (info[j >> 5] >> (j & 31)) & 1u;
+                else if (j != 0xFFFFu) bit = (crcbits >> (j - a.K)) & 1u;
+                word |= bit << i;
+            }
+            u[w] = word;
+        }
+        __syncwarp();
+        // x = u F^(x)n: in-word stages, then word-level stages (PolarCode.cpp:76-83)
+        for (int w = lane; w < NW; w += 32) {
+            uint32_t x = u[w];
+            if (N > 1) x ^= (x >> 1) & 0x55555555u;
+            if (N > 2) x ^= (x >> 2) & 0x33333333u;
+            if (N > 4) x ^= (x >> 4) & 0x0F0F0F0Fu;
+            if (N > 8) x ^= (x >> 8) & 0x00FF00FFu;
+            if (N > 16) x ^= (x >> 16) & 0x0000FFFFu;
+            u[w] = x;
+        }
+        __syncwarp();
+        for (int sw = 1; sw < NW; sw <<= 1) {
+            for (int w = lane; w < NW; w += 32)
+                if ((w & sw) == 0) u[w] ^= u[w + sw];
+            __syncwarp();
+        }
+        // coded[i] = x[bitrev(i)] (PolarCode.cpp:85-87), BPSK 0 -> -1, r = a s + sqrt(1/2) z, llr = -4 r a (:747,:752)
+        const float amp = a.amp[(int)(gidx % (unsigned long long)a.n_ebno)];
+        float* out = a.llr + (size_t)b * N;
+        for (int i4 = lane; i4 * 4 < N; i4 += 32) {
+            uint32_t r[4];
+            philox4x32_10(g0, g1, (uint32_t)i4, 1u, k0, k1, r);       // draw index space 1: noise
+            float z[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
+                const float u2 = ((float)(r[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+                const float rad = sqrtf(-2.0f * __logf(u1));
+                float sn, cs;
+                __sincosf(6.283185307179586f * u2, &sn, &cs);
+                z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int i = i4 * 4 + q;
+                if (i < N) {
+                    const unsigned p = a.n ? (__brev((unsigned)i) >> (32 - a.n)) : 0u;
+                    const float c = (float)((u[p >> 5] >> (p & 31)) & 1u);
+                    const float rx = amp * (2.0f * c - 1.0f) + 0.70710678118654752f * z[q];
+                    out[i] = -4.0f * rx * amp;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     if (!s || !*s) return dflt;
@@ -437,6 +565,9 @@ struct polar_b200_ctx {
     uint32_t* d_frozen = nullptr;
     uint16_t* d_order = nullptr;
     uint32_t* d_crc_masks = nullptr;
+    uint16_t* d_inv_order = nullptr;       // synth: decoding position -> info / parity index
+    uint32_t* d_crc_rows = nullptr;        // synth: parity matrix rows packed over the info index
+    float* d_amp = nullptr;                // synth: per-Eb/N0 amplitudes (up to 64)
     float* d_gx = nullptr;
     uint32_t* d_gs = nullptr;
     size_t gx_stride = 0, gs_stride = 0;   // per warp, elements
@@ -727,6 +858,19 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
     if ((rc = (int)cudaMemcpy(c->d_frozen, fw.data(), fw.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
     if ((rc = (int)cudaMemcpy(c->d_order, info_order, (size_t)(K + crc_bits) * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
     if ((rc = (int)cudaMemcpy(c->d_crc_masks, cm.data(), cm.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+    {
+        std::vector<uint16_t> inv(N, 0xFFFF);
+        for (int j = 0; j < K + crc_bits; ++j) inv[info_order[j]] = (uint16_t)j;
+        std::vector<uint32_t> rows((size_t)(crc_bits ? crc_bits : 1) * c->KW, 0);
+        for (int r = 0; r < crc_bits; ++r)
+            for (int j = 0; j < K; ++j)
+                if (crc_matrix[(size_t)r * K + j] & 1) rows[(size_t)r * c->KW + (j >> 5)] |= 1u << (j & 31);
+        if ((rc = (int)cudaMalloc(&c->d_inv_order, (size_t)N * 2)) != 0) return fail(rc);
+        if ((rc = (int)cudaMalloc(&c->d_crc_rows, rows.size() * 4)) != 0) return fail(rc);
+        if ((rc = (int)cudaMalloc(&c->d_amp, 64 * sizeof(float))) != 0) return fail(rc);
+        if ((rc = (int)cudaMemcpy(c->d_inv_order, inv.data(), (size_t)N * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+        if ((rc = (int)cudaMemcpy(c->d_crc_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+    }
     if ((rc = (int)cudaMalloc(&c->d_llr_stage, (size_t)max_batch * N * sizeof(float))) != 0) return fail(rc);
     if ((rc = (int)cudaMalloc(&c->d_out_stage, (size_t)max_batch * c->KW * sizeof(uint32_t))) != 0) return fail(rc);
     *out = c;
@@ -737,6 +881,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     if (!c) return POLAR_B200_E_ARG;
     cudaSetDevice(c->device);
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
+    cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs);
     if (c->st_h2d) {
@@ -845,6 +990,30 @@ int polar_b200_count_errors(polar_b200_ctx* c, const uint32_t* info_packed, cons
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     count_errors_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)cuda_stream>>>(info_packed, truth_packed, B, c->KW, block_err, n_err);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_synthesize(polar_b200_ctx* c, unsigned long long seed, long long first_index, int B,
+                          const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed, void* cuda_stream) {
+    if (!c || !ebno_db || !llr || !truth_packed || B < 0 || n_ebno < 1 || n_ebno > 64 || first_index < 0) return POLAR_B200_E_ARG;
+    if (c->K > 2048 || c->N > 8192) return POLAR_B200_E_UNSUPPORTED;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    float amp[64];
+    for (int i = 0; i < n_ebno; ++i)      // PolarCode.cpp:744-745
+        amp[i] = (float)(pow(10.0, ebno_db[i] / 20.0) * sqrt((double)c->K / (double)c->N));
+    CU_TRY(cudaMemcpyAsync(c->d_amp, amp, n_ebno * sizeof(float), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));    // amp[] is a stack buffer
+    SynthArgs a;
+    a.llr = llr; a.truth = truth_packed; a.inv_order = c->d_inv_order; a.crc_rows = c->d_crc_rows; a.amp = c->d_amp;
+    a.seed = seed; a.first_index = first_index; a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.n_ebno = n_ebno;
+    int blocks = (B + 3) / 4;
+    const int cap = c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    synth_kernel<<<blocks, 128, 0, st>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     return POLAR_B200_OK;

@@ -231,3 +231,48 @@ def test_unmodified_reference_main_prints_the_reference_table(torch_cuda):
     print("BLER cells identical to the reference: %d / 25; max |diff| %.6f" % (same, np.abs(got_t - want_t).max()))
     assert same >= 20
     assert np.abs(got_t - want_t).max() <= 0.01
+
+
+def test_device_front_end_matches_reference_encoder_and_channel(torch_cuda):
+    """polar_b200_synthesize: (a) at a very high Eb/N0 the hard decisions of the LLRs are the reference
+    encoder's codeword for the reported info bits (PolarCode.cpp:60-91, 715, 752); (b) a codeword depends
+    only on (seed, index), not on batching; (c) the noise is N(0, 1/2) per PolarCode.cpp:747; (d) the
+    decoder gets the info bits back."""
+    torch = torch_cuda
+    from polar_b200 import PolarCode, unpack_bits
+    for (n, K, crc) in [(9, 256, 16), (11, 1024, 16), (7, 64, 0), (10, 500, 8)]:
+        pc, port = PolarCode(n, K, 0.32, crc), Port(n, K, 0.32, crc)
+        N = 1 << n
+        llr, truth = pc.synthesize(300, [60.0], seed=42)
+        info = unpack_bits(truth.cpu().numpy().view(np.uint32), K)
+        coded = port.encode(info)
+        hard = (llr.cpu().numpy() < 0).astype(np.uint8)
+        assert np.array_equal(hard, coded)
+        # (b) same indices in two differently sized calls
+        llr2, truth2 = pc.synthesize(100, [60.0], seed=42, first_index=150)
+        assert torch.equal(llr2, llr[150:250]) and torch.equal(truth2, truth[150:250])
+        # (c) noise statistics at 2 dB: z = (llr / (-4a) - a s) / sqrt(1/2)
+        llr3, truth3 = pc.synthesize(2000, [2.0], seed=7)
+        info3 = unpack_bits(truth3.cpu().numpy().view(np.uint32), K)
+        s = 2.0 * port.encode(info3[:200]).astype(np.float64) - 1.0
+        a = 10.0 ** (2.0 / 20.0) * np.sqrt(K / N)
+        z = (llr3[:200].cpu().numpy().astype(np.float64) / (-4.0 * a) - a * s) / np.sqrt(0.5)
+        assert abs(z.mean()) < 0.02 and abs(z.var() - 1.0) < 0.03 and abs((z ** 4).mean() - 3.0) < 0.2
+        # (d) round trip through the decoder at a comfortable Eb/N0
+        llr4, truth4 = pc.synthesize(512, [4.0], seed=9)
+        out = pc.decode_device(llr4, 8)
+        assert int((out != truth4).any(dim=1).sum().item()) <= 2
+
+
+def test_device_bler_sweep_agrees_with_host_sweep(torch_cuda):
+    """the all-on-GPU sweep and the host-generated sweep estimate the same BLER (different RNGs, so
+    agreement is statistical: 5 sigma of the binomial difference)."""
+    from polar_b200 import PolarCode, bler
+    pc = PolarCode(9, 256, 0.32, 16)
+    ebno, lists, total = [1.0, 2.0], [1, 8], 2048
+    dev = bler.sweep_counts_device(pc, lists, ebno, total, seed=5)
+    host = bler.sweep_counts(pc, lambda llr, L: pc.decode_batch(llr, L), lists, ebno, total, seed=5)
+    assert np.all(dev[..., 1] == total) and np.all(host[..., 1] == total)
+    p1, p2 = dev[..., 0] / total, host[..., 0] / total
+    sigma = np.sqrt((p1 * (1 - p1) + p2 * (1 - p2)) / total) + 1e-4
+    assert np.all(np.abs(p1 - p2) <= 5 * sigma)
