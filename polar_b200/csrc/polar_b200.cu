@@ -662,7 +662,7 @@ int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p) {
 
 // ---- fast-kernel variants (scl_fast.cuh) ----
 struct FastVariant {
-    int nlog, T, lamS, wpb, bps;
+    int nlog, T, lamS, wlog, wpb, bps;
     size_t gx_floats, gs_words;
     int smem_per_warp;
     cudaError_t (*launch)(const fast::Args&, int blocks, cudaStream_t st, const cudaLaunchAttribute* attrs, int nattrs);
@@ -683,41 +683,39 @@ cudaError_t prepare_fast() {
     return cudaFuncSetAttribute(fast::scl_fast_kernel<C, WPB, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 C::SMEM_PER_WARP * WPB);
 }
-#define POLAR_FAST(NLOG, T, LAMS, WPB, BPS)                                                              \
-    { NLOG, T, LAMS, WPB, BPS, fast::Cfg<NLOG, T, LAMS>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS>::GS_WORDS,   \
-      fast::Cfg<NLOG, T, LAMS>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS>,           \
-      prepare_fast<fast::Cfg<NLOG, T, LAMS>, WPB, BPS> }
+#define POLAR_FAST(NLOG, T, LAMS, WLOG, WPB, BPS)                                                                   \
+    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG>::GS_WORDS, \
+      fast::Cfg<NLOG, T, LAMS, WLOG>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS>,               \
+      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS> }
 
-// pick_fast_variant() chooses the default per block length; POLAR_B200_FAST_VARIANT=<index> overrides
+// (log2 N, virtual top layers, first shared-memory layer, log2 lanes per codeword, warps/block, blocks/SM).
+// pick_fast_variant() takes the first entry matching (n, lanes); POLAR_B200_FAST_VARIANT=<index> overrides.
 const FastVariant kFastVariants[] = {
-    POLAR_FAST(11, 3, 5, 4, 3),    // 0: N=2048, layers 3-4 in HBM scratch, 5-6 shared, 12 warps/SM
-    POLAR_FAST(11, 3, 6, 4, 5),    // 1: N=2048, layers 3-5 in HBM scratch, 6 shared, 20 warps/SM
-    POLAR_FAST(9, 3, 3, 4, 4),     // 2: N=512, layers 3-4 shared, 16 warps/SM
-    POLAR_FAST(9, 3, 4, 4, 5),     // 3: N=512, layer 3 in HBM scratch, 20 warps/SM
-    POLAR_FAST(10, 3, 4, 4, 4),    // 4: N=1024
-    POLAR_FAST(12, 3, 6, 4, 4),    // 5: N=4096
-    POLAR_FAST(8, 3, 3, 4, 4),     // 6: N=256
-    POLAR_FAST(11, 3, 5, 4, 4),    // 7: as 0 with 16 warps/SM (128 registers)
-    POLAR_FAST(11, 3, 6, 4, 4),    // 8: as 1 with 16 warps/SM
-    POLAR_FAST(11, 3, 5, 5, 3),    // 9: as 0 with 15 warps/SM (shared-memory limit)
-    POLAR_FAST(11, 4, 5, 4, 4),    // 10: top 4 layers virtual, layer 4 in HBM scratch, 16 warps/SM
-    POLAR_FAST(11, 4, 6, 4, 5),    // 11: top 4 layers virtual, layers 4-5 in HBM scratch, 20 warps/SM
-    POLAR_FAST(11, 4, 5, 5, 3),    // 12: top 4 layers virtual, layer 4 in HBM scratch, 15 warps/SM
-    POLAR_FAST(11, 3, 6, 3, 6),    // 13: as 1 with 18 warps/SM (112 registers)
-    POLAR_FAST(11, 3, 5, 3, 5),    // 14: as 0 with 15 warps/SM (136 registers)
+    POLAR_FAST(11, 3, 5, 5, 4, 4),   // 0: N=2048, lists 17..32: layers 3-4 in HBM scratch, 5-6 shared, 16 warps/SM
+    POLAR_FAST(11, 3, 6, 5, 4, 5),   // 1: N=2048, lists 17..32: layers 3-5 in HBM scratch, 20 warps/SM
+    POLAR_FAST(11, 3, 5, 4, 4, 4),   // 2: N=2048, lists 9..16 (2 codewords per warp)
+    POLAR_FAST(11, 3, 5, 3, 4, 4),   // 3: N=2048, lists 5..8  (4 codewords per warp)
+    POLAR_FAST(11, 3, 5, 2, 4, 4),   // 4: N=2048, lists 3..4  (8 codewords per warp)
+    POLAR_FAST(9, 3, 4, 5, 4, 5),    // 5: N=512, lists 17..32: layer 3 in HBM scratch, 20 warps/SM
+    POLAR_FAST(9, 3, 4, 4, 4, 5),    // 6: N=512, lists 9..16
+    POLAR_FAST(9, 3, 4, 3, 4, 5),    // 7: N=512, lists 5..8
+    POLAR_FAST(9, 3, 4, 2, 4, 5),    // 8: N=512, lists 3..4
+    POLAR_FAST(10, 3, 4, 5, 4, 4),   // 9: N=1024, lists 17..32
+    POLAR_FAST(12, 3, 6, 5, 4, 4),   // 10: N=4096, lists 17..32
+    POLAR_FAST(8, 3, 3, 5, 4, 4),    // 11: N=256, lists 17..32
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
 int pick_fast_variant(int n, int L) {
     if (env_int("POLAR_B200_FORCE_GENERIC", 0)) return -1;
-    if (L <= env_int("POLAR_B200_FAST_MIN_L", 16)) return -1;   // smaller lists: several codewords per warp (generic kernel)
+    int wlog = 2;
+    while ((1 << wlog) < L) ++wlog;                 // lanes per codeword; lists 1..2 stay on the generic kernel
+    if (L < 3 || wlog > 5) return -1;
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
-    if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n) return forced;
-    // measured best per block length (profiles/): N=2048 -> variant 7, N=512 -> variant 3
-    const int preferred = (n == 11) ? 7 : (n == 9) ? 3 : -1;
-    if (preferred >= 0) return preferred;
+    if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n && kFastVariants[forced].wlog == wlog)
+        return forced;
     for (int i = 0; i < kNumFastVariants; ++i)
-        if (kFastVariants[i].nlog == n) return i;
+        if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog) return i;
     return -1;
 }
 
@@ -761,10 +759,11 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
         const int mt = (1 << v.nlog) >> v.T;
         int pa = (c->first_info / 16) * 16;
         if (pa > mt - 16) pa = mt - 16;
-        if (pa < 0 || env_int("POLAR_B200_PHASE_A", 1) == 0) pa = 0;
+        if (pa < 0 || v.wlog != 5 || env_int("POLAR_B200_PHASE_A", 1) == 0) pa = 0;
         a.PA = pa;
     }
-    const int need = (B + v.wpb - 1) / v.wpb;
+    const int cw_per_block = v.wpb * (32 >> v.wlog);
+    const int need = (B + cw_per_block - 1) / cw_per_block;
     if (blocks > need) blocks = need;
     cudaLaunchAttribute attr[1];
     int nattr = 0;
@@ -949,7 +948,7 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
     {
         const int fv = pick_fast_variant(c->n, L);
         if (fv >= 0) {
-            per_round = c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb;
+            per_round = c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);
         } else {
             LaunchPlan p = make_plan(c);
             int W = 1; while (W < L) W <<= 1;

@@ -28,9 +28,12 @@
 
 namespace fast {
 
-template <int NLOG_, int T_, int LAMS_>
+template <int NLOG_, int T_, int LAMS_, int WLOG_ = 5>
 struct Cfg {
-    static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_;
+    static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_, WLOG = WLOG_;
+    static constexpr int W = 1 << WLOG;               // lanes per codeword (list size rounded up to a power of two)
+    static constexpr int G = 32 / W;                  // codewords per warp
+    static_assert(WLOG >= 2 && WLOG <= 5, "4..32 lanes per codeword");
     static constexpr int N = 1 << NLOG;
     static constexpr int MT = N >> T;                 // rows of the first per-path layer
     static constexpr int NW = N / 32;
@@ -59,7 +62,7 @@ struct Cfg {
     static constexpr int SS_ROWS = ss_rows();
     static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64;
     static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
-    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + XS_FLOATS + PA_FLOATS;
+    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + (size_t)G * XS_FLOATS + PA_FLOATS;
     static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
 };
 
@@ -80,10 +83,10 @@ struct Warp {          // per-warp pointers
     uint32_t* ss;      // shared partial-sum rows
     unsigned char* srcof;   // clone scatter: srcof[new lane] = parent lane
     unsigned char* stack;   // free-path stack (PolarCode.h:60 _inactivePathIndices)
-    float* gx;         // HBM LLR rows, followed by XS
-    float* xs;         // shared compact arrays
+    float* gx;         // HBM LLR rows, followed by the XS arrays of the warp's codewords
+    float* xs;         // compact shared arrays of THIS LANE's codeword
     uint32_t* gs;      // HBM partial-sum rows
-    const float* chan;
+    const float* chan; // channel LLRs of THIS LANE's codeword
     int lane;
 };
 
@@ -105,6 +108,32 @@ constexpr __host__ __device__ int lead_zeros(int node, int bits) {
     int z = 0;
     for (int b = bits - 1; b >= 0; --b) { if (node & (1 << b)) break; ++z; }
     return z;
+}
+
+// reductions / ballots over the W lanes of one codeword
+template <int W> __device__ __forceinline__ unsigned gmin(unsigned v) {
+    if constexpr (W == 32) return __reduce_min_sync(FULL_MASK, v);
+    else {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL_MASK, v, o));
+        return v;
+    }
+}
+template <int W> __device__ __forceinline__ unsigned gmax(unsigned v) {
+    if constexpr (W == 32) return __reduce_max_sync(FULL_MASK, v);
+    else {
+#pragma unroll
+        for (int o = W / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL_MASK, v, o));
+        return v;
+    }
+}
+template <int W> __device__ __forceinline__ unsigned gballot(bool p, int gbase) {
+    const unsigned b = __ballot_sync(FULL_MASK, p);
+    if constexpr (W == 32) return b;
+    else return (b >> gbase) & ((1u << W) - 1u);
+}
+template <class P> __device__ __forceinline__ P* shfl_ptr(P* p, int src) {
+    return reinterpret_cast<P*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(p), src));
 }
 
 template <class C, int LAM>
@@ -324,26 +353,37 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
 
 // ---- node 0 of layer T: one path exists, the warp works across beta; fills XS_1..XS_T ----
 template <class C>
-__device__ __forceinline__ void top_solo(const Warp& w, int c0) {
+__device__ __forceinline__ void top_solo_one(const Warp& w, const float* chan, float* xs, int c0) {
     constexpr int T = C::T, N = C::N, NLOG = C::NLOG;
-    float* xs1 = w.xs + C::xs_off(1);
+    float* xs1 = xs + C::xs_off(1);
     for (int k = w.lane; k < N / 2; k += 32) {
-        const float2 c = __ldg(reinterpret_cast<const float2*>(w.chan) + k);
+        const float2 c = __ldg(reinterpret_cast<const float2*>(chan) + k);
         xs1[brev_bits(k, NLOG - 1)] = f_rule(c.x, c.y);
     }
     __syncwarp();
 #pragma unroll
     for (int lev = 2; lev <= T; ++lev) {
-        const float* in = w.xs + C::xs_off(lev - 1);
-        float* out = w.xs + C::xs_off(lev);
+        const float* in = xs + C::xs_off(lev - 1);
+        float* out = xs + C::xs_off(lev);
         const int M = N >> lev;
         for (int b = w.lane; b < M; b += 32) out[b] = f_rule(in[b], in[b + M]);
         __syncwarp();
     }
-    const float* xt = w.xs + C::xs_off(T);
+    const float* xt = xs + C::xs_off(T);
     float* col = xbase<C, T>(w) + c0;
     for (int b = w.lane; b < C::MT; b += 32) col[b * 32] = xt[b];
     __syncwarp();
+}
+// all codewords of the warp, one after the other (c0 = local index of the first path)
+template <class C>
+__device__ __forceinline__ void top_solo(const Warp& w, int c0, bool valid) {
+#pragma unroll 1
+    for (int g = 0; g < C::G; ++g) {
+        const float* chan = shfl_ptr(w.chan, g * C::W);
+        float* xs = shfl_ptr(w.xs, g * C::W);
+        const bool ok = __shfl_sync(FULL_MASK, (int)valid, g * C::W);
+        if (ok) top_solo_one<C>(w, chan, xs, g * C::W + c0);
+    }
 }
 
 // ---- phase A: the leading PA leaves are frozen and only one path exists, so the warp decodes them
@@ -357,7 +397,7 @@ template <class C>
 __device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
     constexpr int T = C::T, LB = C::LB, MT = C::MT, N = C::N;
     const int lane = w.lane;
-    top_solo<C>(w, c0);
+    top_solo_one<C>(w, w.chan, w.xs, c0);
     float* bufA = w.xs + C::XS_FLOATS;
     float* bufB = bufA + MT / 2;
     float* V = bufB + MT / 2;
@@ -414,14 +454,14 @@ __device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
 // refresh everything above the register subtree for the 16-leaf block starting at phi0, ending with
 // the 16 LLRs of layer NLOG-4 in registers (PolarCode.cpp:422-455 for the layers involved)
 template <class C>
-__device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, int phi0, int c0) {
+__device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, int phi0, int c0, bool valid) {
     constexpr int T = C::T, NLOG = C::NLOG, LB = C::LB;
     const int lam_top = (phi0 == 0) ? 0 : NLOG - (__ffs(phi0) - 1);      // <= LB
     bool first = true;
     if (lam_top <= T) {
         const int node = phi0 >> (NLOG - T);
         switch (node) {
-            case 0: top_solo<C>(w, c0); s.px = set_ptr(s.px, 0, c0); break;
+            case 0: top_solo<C>(w, c0, valid); s.px = set_ptr(s.px, 0, (w.lane & ~(C::W - 1)) + c0); break;
 #define POLAR_TN(N_) case N_: if constexpr (N_ < (1 << T)) top_node<C, N_>(w, s); break;
             POLAR_TN(1) POLAR_TN(2) POLAR_TN(3) POLAR_TN(4) POLAR_TN(5) POLAR_TN(6) POLAR_TN(7)
             POLAR_TN(8) POLAR_TN(9) POLAR_TN(10) POLAR_TN(11) POLAR_TN(12) POLAR_TN(13) POLAR_TN(14) POLAR_TN(15)
@@ -448,12 +488,14 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
     else layer_to_regs<C, false>(w, s, r);
 }
 
-// ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607), 32 lanes = one codeword ----
-// Returns the decided bit of this lane's (possibly new) path.
+// ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607); W lanes = the list of one codeword ----
+// Returns the decided bit of this lane's (possibly new) path. `permuted` is warp-uniform.
 template <class C>
 __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp, bool& permuted,
                                               int& src_lane) {
+    constexpr int W = C::W;
     const int lane = w.lane;
+    const int gbase = lane & ~(W - 1), slot = lane & (W - 1);
     // both fork metrics from one log1p(exp(-|x|)) (softplus_ref(-|x|) and softplus_ref(+|x|))
     const float ax = fabsf(lam_n);
     const float t = log1p_exp_neg(ax);
@@ -461,67 +503,102 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     const float mhi = s.pm + ((ax >= 709.78271484375f) ? CUDART_INF_F : ax + t);  // unlikely fork
     const bool neg = lam_n < 0.0f;
     const float m0 = neg ? mhi : mlo, m1 = neg ? mlo : mhi;
-    const unsigned act = __ballot_sync(FULL_MASK, s.active);
+    const unsigned act = gballot<W>(s.active, gbase);
     const int A = __popc(act);
     permuted = false;
     src_lane = lane;
     bool keep0 = s.active, keep1 = s.active;
-    if (2 * A > L) {
-        // keep the L best forks under (metric asc, fork index asc). Metrics are >= 0: uint order = float order.
-        const unsigned klo = __float_as_uint(mlo), khi = __float_as_uint(mhi);
-        if (A == L) {
-            // common exit: every unlikely fork is strictly worse than every likely fork
-            const unsigned kb = __reduce_min_sync(FULL_MASK, s.active ? khi : 0xFFFFFFFFu);
-            const unsigned ka = __reduce_max_sync(FULL_MASK, s.active ? klo : 0u);
-            if (kb > ka) {
-                if (s.active) s.pm = mlo;
-                return (m1 < m0) ? 1u : 0u;
+    // keep the L best forks under (metric asc, fork index asc). Metrics are >= 0: uint order = float order.
+    const unsigned klo = __float_as_uint(mlo), khi = __float_as_uint(mhi);
+    const bool like1 = m1 < m0;                            // likely fork is bit 1
+    if constexpr (W == 32) {
+        if (2 * A > L) {
+            if (A == L) {
+                // common exit: every unlikely fork is strictly worse than every likely fork
+                const unsigned kb = gmin<W>(s.active ? khi : 0xFFFFFFFFu);
+                const unsigned ka = gmax<W>(s.active ? klo : 0u);
+                if (kb > ka) {
+                    if (s.active) s.pm = mlo;
+                    return like1 ? 1u : 0u;
+                }
             }
+            const unsigned lk = __ballot_sync(FULL_MASK, like1);
+            unsigned keptA = act, keptB = 0;
+            int count = A;
+            while (true) {
+                const unsigned candB = act & ~keptB;
+                if (candB == 0) break;
+                const unsigned kb = gmin<W>(((candB >> lane) & 1u) ? khi : 0xFFFFFFFFu);
+                const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
+                const int bl = __ffs(eqb) - 1;             // lowest lane = lowest fork index among equals
+                if (count < L) { keptB |= 1u << bl; ++count; continue; }
+                const unsigned ka = gmax<W>(((keptA >> lane) & 1u) ? klo : 0u);
+                const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
+                const int al = 31 - __clz(eqa);            // highest lane = highest fork index among equals
+                const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
+                const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
+                const bool better = (kb < ka) || (kb == ka && idxb < idxa);
+                if (!better) break;
+                keptB |= 1u << bl;
+                keptA &= ~(1u << al);
+            }
+            const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
+            keep0 = like1 ? kb_ : ka_;
+            keep1 = like1 ? ka_ : kb_;
         }
-        const bool like1 = m1 < m0;                        // likely fork is bit 1
-        const unsigned lk = __ballot_sync(FULL_MASK, like1);
+    } else {
+        // several codewords per warp: every lane runs the same rounds, a codeword that is finished idles
+        const unsigned lk = gballot<W>(like1, gbase);
         unsigned keptA = act, keptB = 0;
         int count = A;
+        bool done = !(2 * A > L);
         while (true) {
             const unsigned candB = act & ~keptB;
-            if (candB == 0) break;
-            const unsigned kb = __reduce_min_sync(FULL_MASK, ((candB >> lane) & 1u) ? khi : 0xFFFFFFFFu);
-            const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
-            const int bl = __ffs(eqb) - 1;                 // lowest lane = lowest fork index among equals
-            if (count < L) { keptB |= 1u << bl; ++count; continue; }
-            const unsigned ka = __reduce_max_sync(FULL_MASK, ((keptA >> lane) & 1u) ? klo : 0u);
-            const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
-            const int al = 31 - __clz(eqa);                // highest lane = highest fork index among equals
-            const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
-            const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
-            const bool better = (kb < ka) || (kb == ka && idxb < idxa);
-            if (!better) break;
-            keptB |= 1u << bl;
-            keptA &= ~(1u << al);
+            if (!done && candB == 0) done = true;
+            if (!__any_sync(FULL_MASK, !done)) break;
+            const bool cb = (candB >> slot) & 1u, ca = (keptA >> slot) & 1u;
+            const unsigned kb = gmin<W>(cb ? khi : 0xFFFFFFFFu);
+            const unsigned eqb = gballot<W>(cb && khi == kb, gbase);
+            const unsigned ka = gmax<W>(ca ? klo : 0u);
+            const unsigned eqa = gballot<W>(ca && klo == ka, gbase);
+            if (!done) {
+                const int bl = __ffs(eqb) - 1;
+                if (count < L) { keptB |= 1u << bl; ++count; }
+                else {
+                    const int al = 31 - __clz(eqa);
+                    const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
+                    const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
+                    const bool better = (kb < ka) || (kb == ka && idxb < idxa);
+                    if (!better) done = true;
+                    else { keptB |= 1u << bl; keptA &= ~(1u << al); }
+                }
+            }
         }
-        const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
-        keep0 = like1 ? kb_ : ka_;
-        keep1 = like1 ? ka_ : kb_;
+        if (2 * A > L) {
+            const bool ka_ = (keptA >> slot) & 1u, kb_ = (keptB >> slot) & 1u;
+            keep0 = like1 ? kb_ : ka_;
+            keep1 = like1 ? ka_ : kb_;
+        }
     }
     const bool kill = s.active && !keep0 && !keep1;
     const bool clone = keep0 && keep1;
-    const unsigned Kg = __ballot_sync(FULL_MASK, kill);
-    const unsigned Cg = __ballot_sync(FULL_MASK, clone);
     uint32_t u = 0;
-    if ((Kg | Cg) == 0) {
+    if (!__any_sync(FULL_MASK, kill || clone)) {
         if (s.active) { u = keep1 ? 1u : 0u; s.pm = keep1 ? m1 : m0; }
         return u;
     }
     permuted = true;
+    const unsigned Kg = gballot<W>(kill, gbase);
+    const unsigned Cg = gballot<W>(clone, gbase);
     const int nk = __popc(Kg), nc = __popc(Cg);
-    const unsigned lt = (1u << lane) - 1u;
-    if (kill) w.stack[sp + __popc(Kg & lt)] = (unsigned char)lane;      // kills pushed in ascending path order
+    const unsigned lt = (1u << slot) - 1u;
+    if (kill) w.stack[gbase + sp + __popc(Kg & lt)] = (unsigned char)slot;   // kills pushed in ascending path order
     const int sp2 = sp + nk;
     w.srcof[lane] = (unsigned char)lane;
     __syncwarp();
-    if (clone) {                                                        // clones pop, for ascending l
-        const int tgt = w.stack[sp2 - 1 - __popc(Cg & lt)];
-        w.srcof[tgt] = (unsigned char)lane;
+    if (clone) {                                                             // clones pop, for ascending l
+        const int tgt = w.stack[gbase + sp2 - 1 - __popc(Cg & lt)];
+        w.srcof[gbase + tgt] = (unsigned char)lane;
     }
     sp = sp2 - nc;
     __syncwarp();
@@ -603,18 +680,22 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     w.ss = reinterpret_cast<uint32_t*>(my + C::SX_ROWS * 128);
     w.srcof = my + (C::SX_ROWS + C::SS_ROWS) * 128;
     w.stack = w.srcof + 32;
+    constexpr int W = C::W, G = C::G;
+    const int gbase = lane & ~(W - 1), slot = lane & (W - 1), grp_in_warp = lane / W;
     w.gx = a.gx + C::GX_FLOATS * gwarp;
-    w.xs = w.gx + (size_t)C::GX_ROWS * 32;
+    w.xs = w.gx + (size_t)C::GX_ROWS * 32 + (size_t)grp_in_warp * C::XS_FLOATS;
     w.gs = a.gs + C::GS_WORDS * gwarp;
     const int L = a.L, KW = (a.K + 31) >> 5;
     const int c0 = L - 1;                          // first path popped from the free stack (PolarCode.cpp:250-263)
 
-    for (int cw = gwarp; cw < a.B; cw += total_warps) {
-        w.chan = a.llr + (size_t)cw * N;
+    for (int grp = gwarp; grp * G < a.B; grp += total_warps) {
+        const int cw = grp * G + grp_in_warp;
+        const bool valid = cw < a.B;
+        w.chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
         Lane s;
-        s.active = (lane == c0);
+        s.active = valid && (slot == c0);
         s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0;
-        w.stack[lane] = (unsigned char)lane;            // free stack 0..L-2 (entries >= sp are don't-care)
+        w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
         __syncwarp();
         int sp = L - 1;
         float lam_n = 0.0f;
@@ -628,7 +709,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         r.x1[0] = r.x1[1] = 0.0f;
 
         bool have_x4 = false;
-        if (a.PA > 0) {
+        if (W == 32 && a.PA > 0) {
             s.pm = phase_a<C>(w, a.PA, c0);              // out of line: runs once per codeword
             const float* x4src = w.xs + C::XS_FLOATS + C::MT;
 #pragma unroll
@@ -638,8 +719,8 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             have_x4 = true;
         }
 #pragma unroll 1
-        for (int phi0 = a.PA; phi0 < N; phi0 += 16) {
-            if (!have_x4) descend_block<C>(w, s, r, phi0, c0);
+        for (int phi0 = (W == 32 ? a.PA : 0); phi0 < N; phi0 += 16) {
+            if (!have_x4) descend_block<C>(w, s, r, phi0, c0, valid);
             have_x4 = false;
             const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
 #pragma unroll 1
@@ -700,26 +781,33 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             if (__popc(acc) & 1) pass = false;
         }
         // ---- final pick, PolarCode.cpp:609-644 ----
-        const unsigned act = __ballot_sync(FULL_MASK, s.active);
-        const unsigned passm = __ballot_sync(FULL_MASK, s.active && pass);
+        const unsigned act = gballot<W>(s.active, gbase);
+        const unsigned passm = gballot<W>(s.active && pass, gbase);
         const bool use_parity = (a.crc != 0) && (passm != 0);
         const bool eligible = s.active && (use_parity ? pass : true) && (s.pm < CUDART_INF_F);
-        const unsigned best = __reduce_min_sync(FULL_MASK, eligible ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
-        const unsigned cand = __ballot_sync(FULL_MASK, eligible && __float_as_uint(s.pm) == best);
+        const unsigned best = gmin<W>(eligible ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
+        const unsigned cand = gballot<W>(eligible && __float_as_uint(s.pm) == best, gbase);
         const int win = cand ? (__ffs(cand) - 1) : 0;
         const bool win_active = (act >> win) & 1u;
         __syncwarp();
-        const uint32_t* U = sbase<C, 0>(w) + win;
-        for (int t = lane; t < KW; t += 32) {               // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
-            uint32_t word = 0;
-            if (win_active) {
-                const int jmax = min(32, a.K - 32 * t);
-                for (int i = 0; i < jmax; ++i) {
-                    const int pos = a.info_order[32 * t + i];
-                    word |= ((U[(pos >> 5) * 32] >> (pos & 31)) & 1u) << i;
+#pragma unroll 1
+        for (int g = 0; g < G; ++g) {
+            const int cwg = grp * G + g;
+            if (cwg >= a.B) break;
+            const int wl = g * W + __shfl_sync(FULL_MASK, win, g * W);
+            const bool wa = __shfl_sync(FULL_MASK, (int)win_active, g * W);
+            const uint32_t* U = sbase<C, 0>(w) + wl;
+            for (int t = lane; t < KW; t += 32) {           // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
+                uint32_t word = 0;
+                if (wa) {
+                    const int jmax = min(32, a.K - 32 * t);
+                    for (int i = 0; i < jmax; ++i) {
+                        const int pos = a.info_order[32 * t + i];
+                        word |= ((U[(pos >> 5) * 32] >> (pos & 31)) & 1u) << i;
+                    }
                 }
+                a.out[(size_t)cwg * KW + t] = word;
             }
-            a.out[(size_t)cw * KW + t] = word;
         }
         __syncwarp();
     }

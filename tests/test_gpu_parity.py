@@ -45,6 +45,14 @@ PARITY = [
     (11, 1024, 0, 8, 256, 1.5),
     (11, 1024, 16, 16, 128, 1.5),
     (10, 512, 8, 8, 256, 1.5),
+    (9, 256, 16, 4, 1001, 1.0),      # several codewords per warp in the fast kernel, ragged batch
+    (9, 256, 0, 8, 515, 1.0),
+    (9, 256, 16, 16, 259, 1.0),
+    (9, 256, 16, 3, 333, 1.0),       # list size not a power of two on 4 lanes
+    (9, 256, 0, 13, 130, 1.0),
+    (11, 1024, 16, 6, 131, 1.25),
+    (11, 1024, 0, 12, 67, 1.25),
+    (11, 1024, 16, 24, 65, 1.25),    # 24 paths on 32 lanes
     (12, 2048, 16, 8, 48, 1.5),
     (7, 64, 8, 3, 333, 0.5),         # list size not a power of two, ragged batch
     (6, 20, 3, 5, 257, -1.0),
