@@ -103,6 +103,19 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* ctx, const float* llr_host, i
                                    uint32_t* info_packed_host, void* cuda_stream);
 
 /*
+ * Reference-precision mode: the same decoder evaluated in double with the reference's literal
+ * formulas (exp/log box-plus below |LLR| = 40, log(1+exp(x)) metrics; PolarCode.cpp:438-446, 483,
+ * 505-506) on double LLRs, i.e. the arithmetic of PolarCode::decode_scl_llr itself. For callers that
+ * need the reference's decisions on near-tied codewords (arithmetic contract); an
+ * order of magnitude slower than the fp32 path (generic kernel, software exp/log).
+ *   llr: [B][N] double, device (first form) or host (second form, synchronous, B <= max_batch).
+ */
+int polar_b200_decode_scl_llr_f64(polar_b200_ctx* ctx, const double* llr, int B, int L,
+                                  uint32_t* info_packed, void* cuda_stream);
+int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* ctx, const double* llr_host, int B, int L,
+                                       uint32_t* info_packed_host, void* cuda_stream);
+
+/*
  * Block-error flags: block_err[b] = 1 iff any of the K info bits differ. Replaces the
  * comparison loop of the BLER harness (PolarCode.cpp:758-764). All device pointers;
  * n_err (device, may be NULL) is incremented by the number of block errors.
@@ -135,7 +148,7 @@ enum {
     POLAR_B200_INFO_BLOCKS = 3,          /* grid size of the last decode launch             */
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
-    POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i */
+    POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode */
     POLAR_B200_INFO_HOST_CHUNKS = 7      /* chunks the last *_host call was pipelined in            */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);

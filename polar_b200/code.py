@@ -103,6 +103,19 @@ class PolarCode:
             return out
         return unpack_bits(out, self.K)
 
+    def decode_batch_f64(self, llr, list_size, packed=False):
+        """Reference-precision mode: [B][N] float64 host LLRs, evaluated in double on the GPU with the
+        reference's literal formulas (include/polar_b200.h: polar_b200_decode_scl_llr_f64_host)."""
+        llr = np.ascontiguousarray(llr, np.float64).reshape(-1, self.N)
+        out = np.zeros((llr.shape[0], self.KW), np.uint32)
+        _lib.check_host(_lib.host().polar_host_decode_batch_packed_f64(self._h, llr.ctypes.data, llr.shape[0],
+                                                                       int(list_size), out.ctypes.data))
+        return out if packed else unpack_bits(out, self.K)
+
+    def set_exact(self, exact=True):
+        """decode_scl_llr / get_bler_quick in reference precision (double) from now on"""
+        _lib.host().polar_host_set_exact(self._h, 1 if exact else 0)
+
     # ---- batched, device memory (torch CUDA tensors), asynchronous on the current stream ----
     def decode_device(self, llr, list_size, out=None, stream=None):
         import torch

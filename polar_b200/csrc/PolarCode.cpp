@@ -23,6 +23,8 @@ void check(int rc, const char* what) {
 
 PolarCode::PolarCode(uint8_t num_layers, uint16_t info_length, double epsilon, uint16_t crc_size)
     : _n(num_layers), _info_length(info_length), _crc_size(crc_size), _design_epsilon(epsilon) {
+    const char* ex = getenv("POLAR_B200_EXACT");
+    exact_arithmetic = ex && *ex && *ex != '0';
     _block_length = (uint16_t)(1 << _n);
     _frozen_bits.resize(_block_length);
     _bit_rev_order.resize(_block_length);
@@ -115,6 +117,12 @@ void PolarCode::decode_scl_llr_batch_packed(const float* llr, int B, uint16_t li
           "polar_b200_decode_scl_llr_host");
 }
 
+void PolarCode::decode_scl_llr_batch_packed_f64(const double* llr, int B, uint16_t list_size, uint32_t* info_packed) {
+    if (list_size >= 128) throw std::invalid_argument("PolarCode: list_size must be < 128");
+    check(polar_b200_decode_scl_llr_f64_host(device_ctx(B), llr, B, list_size, info_packed, nullptr),
+          "polar_b200_decode_scl_llr_f64_host");
+}
+
 std::vector<uint8_t> PolarCode::decode_scl_llr_batch(const float* llr, int B, uint16_t list_size) {
     const int KW = info_words(), K = _info_length;
     std::vector<uint32_t> packed((size_t)B * KW);
@@ -133,6 +141,14 @@ void PolarCode::decode_scl_llr_device(const float* llr_dev, int B, uint16_t list
 
 // PolarCode.cpp:130-148: one codeword by value in, K bytes out.
 std::vector<uint8_t> PolarCode::decode_scl_llr(std::vector<double> llr, uint16_t list_size) {
+    if (exact_arithmetic) {
+        llr.at(_block_length - 1);
+        std::vector<uint32_t> packed(info_words());
+        decode_scl_llr_batch_packed_f64(llr.data(), 1, list_size, packed.data());
+        std::vector<uint8_t> out(_info_length);
+        for (int j = 0; j < _info_length; ++j) out[j] = (packed[j >> 5] >> (j & 31)) & 1u;
+        return out;
+    }
     std::vector<float> f(_block_length);
     for (int i = 0; i < _block_length; ++i) f[i] = (float)llr.at(i);
     return decode_scl_llr_batch(f.data(), 1, list_size);
@@ -180,16 +196,19 @@ std::vector<std::vector<double>> PolarCode::get_bler_quick(std::vector<double> e
 
     // phase 2: ok[l][e][run]
     std::vector<uint8_t> ok(nl * ne * (size_t)max_runs, 0);
-    std::vector<float> llr((size_t)max_runs * N);
+    std::vector<float> llr(exact_arithmetic ? 0 : (size_t)max_runs * N);
+    std::vector<double> llr64(exact_arithmetic ? (size_t)max_runs * N : 0);
     std::vector<uint32_t> dec((size_t)max_runs * KW);
     for (size_t ie = 0; ie < ne; ++ie) {
         const double a = std::pow(10.0f, ebno_vec[ie] / 20) * std::sqrt(((double)K) / ((double)N));
-        for (size_t i = 0; i < llr.size(); ++i) {
+        for (size_t i = 0; i < noise.size(); ++i) {
             const double r = a * (double)bpsk[i] + std::sqrt(N_0 / 2) * noise[i];
-            llr[i] = (float)(-4 * r * a / N_0);
+            const double v = -4 * r * a / N_0;
+            if (exact_arithmetic) llr64[i] = v; else llr[i] = (float)v;
         }
         for (size_t il = 0; il < nl; ++il) {
-            decode_scl_llr_batch_packed(llr.data(), max_runs, list_size_vec[il], dec.data());
+            if (exact_arithmetic) decode_scl_llr_batch_packed_f64(llr64.data(), max_runs, list_size_vec[il], dec.data());
+            else decode_scl_llr_batch_packed(llr.data(), max_runs, list_size_vec[il], dec.data());
             for (int run = 0; run < max_runs; ++run) {
                 bool same = true;
                 for (int w = 0; w < KW; ++w) same &= dec[(size_t)run * KW + w] == truth[(size_t)run * KW + w];
@@ -289,6 +308,13 @@ int polar_host_decode_device(void* h, const float* llr_dev, int B, int L, uint32
     PolarCode* p = static_cast<PolarCode*>(h);
     return guarded([&] { p->decode_scl_llr_device(llr_dev, B, (uint16_t)L, info_packed_dev, stream); });
 }
+
+int polar_host_decode_batch_packed_f64(void* h, const double* llr, int B, int L, uint32_t* info_packed) {
+    PolarCode* p = static_cast<PolarCode*>(h);
+    return guarded([&] { p->decode_scl_llr_batch_packed_f64(llr, B, (uint16_t)L, info_packed); });
+}
+
+void polar_host_set_exact(void* h, int exact) { static_cast<PolarCode*>(h)->exact_arithmetic = exact != 0; }
 
 void* polar_host_ctx(void* h, int min_batch) {
     PolarCode* p = static_cast<PolarCode*>(h);

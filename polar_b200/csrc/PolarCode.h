@@ -45,6 +45,8 @@ public:
     std::vector<uint8_t> decode_scl_llr_batch(const float* llr, int B, uint16_t list_size);
     // Same with packed output: [B][info_words()] little-endian words.
     void decode_scl_llr_batch_packed(const float* llr, int B, uint16_t list_size, uint32_t* info_packed);
+    // Reference-precision mode (double LLRs, the reference's literal formulas in double on the GPU).
+    void decode_scl_llr_batch_packed_f64(const double* llr, int B, uint16_t list_size, uint32_t* info_packed);
     // Device pointers, asynchronous on `cuda_stream` (a cudaStream_t).
     void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream);
 
@@ -64,6 +66,9 @@ public:
     int bler_max_runs = 1000;
     bool bler_verbose = true;      // the reference's "Running iteration ..." lines
     int device = 0;                // CUDA device ordinal
+    // true: decode_scl_llr / get_bler_quick evaluate in double (polar_b200_decode_scl_llr_f64*), an order of
+    // magnitude slower; default false, or true when the environment has POLAR_B200_EXACT=1
+    bool exact_arithmetic = false;
 
 private:
     uint8_t _n;

@@ -46,15 +46,16 @@ constexpr int kMaxN = 13;          // log2 block length supported by the pointer
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-struct DecodeArgs {
-    const float* llr;            // [B][N]
+template <class Real>
+struct DecodeArgsT {
+    const Real* llr;             // [B][N]
     uint32_t* out;               // [B][KW]
     const uint32_t* frozen_words;// [max(1,N/32)], bit phi set = frozen
     const uint16_t* info_order;  // [K + crc]
     const uint32_t* crc_masks;   // [crc][NW] over phi
-    float* gx;                   // per-warp LLR scratch rows (32 floats each)
+    Real* gx;                    // per-warp LLR scratch rows (32 values each)
     uint32_t* gs;                // per-warp partial-sum scratch rows (32 words each)
-    unsigned long long gx_stride;// floats per warp
+    unsigned long long gx_stride;// values per warp
     unsigned long long gs_stride;// words per warp
     int B, n, K, crc, L;
     int W;                       // lanes per codeword (power of two >= L)
@@ -106,12 +107,36 @@ __device__ __forceinline__ float softplus_ref(float x) {
     return r;
 }
 
-__device__ __forceinline__ float group_min(float v, int W) {
-    for (int o = W >> 1; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL_MASK, v, o));
+
+// ---- arithmetic by evaluation type. float: the throughput contract above. double: the reference's
+// literal formulas (PolarCode.cpp:438-446, 483, 505-506) evaluated in double like the reference itself.
+template <class Real> struct Arith;
+template <> struct Arith<float> {
+    static __device__ __forceinline__ float f(float a, float b) { return f_rule(a, b); }
+    static __device__ __forceinline__ float softplus(float x) { return softplus_ref(x); }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+};
+template <> struct Arith<double> {
+    static __device__ __forceinline__ double f(double a, double b) {
+        const double ma = fabs(a), mb = fabs(b);
+        if (40.0 > fmax(ma, mb)) return log((exp(a + b) + 1.0) / (exp(a) + exp(b)));
+        const double sa = (a < 0) ? -1.0 : (double)(a > 0), sb = (b < 0) ? -1.0 : (double)(b > 0);
+        return sa * sb * fmin(ma, mb);
+    }
+    static __device__ __forceinline__ double softplus(double x) { return log(1.0 + exp(x)); }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+};
+template <class Real> __device__ __forceinline__ Real rmin(Real a, Real b) { return a < b ? a : b; }
+template <class Real> __device__ __forceinline__ Real rmax(Real a, Real b) { return a > b ? a : b; }
+
+template <class Real>
+__device__ __forceinline__ Real group_min(Real v, int W) {
+    for (int o = W >> 1; o > 0; o >>= 1) v = rmin<Real>(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
 }
-__device__ __forceinline__ float group_max(float v, int W) {
-    for (int o = W >> 1; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(FULL_MASK, v, o));
+template <class Real>
+__device__ __forceinline__ Real group_max(Real v, int W) {
+    for (int o = W >> 1; o > 0; o >>= 1) v = rmax<Real>(v, __shfl_xor_sync(FULL_MASK, v, o));
     return v;
 }
 
@@ -131,7 +156,9 @@ namespace {
 //   smem_x_rows rows of 32 floats (LLR layers lamS..n-1), smem_s_rows rows of 32 words
 //   (partial-sum layers >= max(lamS,1), except layer n which is a register), 32 bytes of scatter
 //   scratch.
-__global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
+template <class Real>
+__global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real> a) {
+    constexpr int ROWB = 32 * (int)sizeof(Real);         // bytes of one [32 lanes] row
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
@@ -147,16 +174,16 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
     const int NW = (N + 31) >> 5;              // words in an N-bit vector
     const int KW = (a.K + 31) >> 5;
 
-    const size_t per_warp_smem = (size_t)(a.smem_x_rows + a.smem_s_rows) * 128 + 32;
+    const size_t per_warp_smem = (size_t)a.smem_x_rows * ROWB + (size_t)a.smem_s_rows * 128 + 32;
     unsigned char* my_smem = smem_raw + per_warp_smem * warp_in_block;
-    float* sx = reinterpret_cast<float*>(my_smem);
-    uint32_t* ss = reinterpret_cast<uint32_t*>(my_smem + (size_t)a.smem_x_rows * 128);
-    unsigned char* srcof = my_smem + (size_t)(a.smem_x_rows + a.smem_s_rows) * 128;
-    float* gx = a.gx + a.gx_stride * gwarp;
+    Real* sx = reinterpret_cast<Real*>(my_smem);
+    uint32_t* ss = reinterpret_cast<uint32_t*>(my_smem + (size_t)a.smem_x_rows * ROWB);
+    unsigned char* srcof = my_smem + (size_t)a.smem_x_rows * ROWB + (size_t)a.smem_s_rows * 128;
+    Real* gx = a.gx + a.gx_stride * gwarp;
     uint32_t* gs = a.gs + a.gs_stride * gwarp;
 
     // Row address of LLR layer lam (1 <= lam <= n-1), position beta.
-    auto xrow = [&](int lam, int beta) -> float* {
+    auto xrow = [&](int lam, int beta) -> Real* {
         if (lam >= lamS) return sx + ((size_t)((1 << (n - lamS + 1)) - (1 << (n - lam + 1)) + beta) << 5);
         return gx + ((size_t)(N - (1 << (n - lam + 1)) + beta) << 5);
     };
@@ -170,17 +197,17 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
     for (int grp = gwarp; grp * G < a.B; grp += total_warps) {
         const int cw = grp * G + (lane / W);
         const bool valid = cw < a.B;
-        const float* chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
+        const Real* chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
 
         // Per-path state. Reference bookkeeping reproduced: the free-path stack is filled
         // 0..L-1 (PolarCode.cpp:250-256) and the first path popped is L-1 (:259-263).
         bool active = valid && (slot == L - 1);
-        float pm = 0.0f;
+        Real pm = 0;
         unsigned long long px = 0, ps = 0;      // column pointers, 5 bits per layer (index lam-1)
         uint32_t s_n = 0;                       // partial sum of layer n (the last even leaf's bit)
         int stk = slot;                         // lane gbase+j holds free-path stack entry j
         int sp = L - 1;                         // stack height (uniform within a codeword)
-        float lam_n = 0.0f;                     // LLR of layer n (decision LLR)
+        Real lam_n = 0;                        // LLR of layer n (decision LLR)
         uint32_t frozen_word = 0;
 
         for (int phi = 0; phi < N; ++phi) {
@@ -189,33 +216,32 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
             for (int lam = lam_top; lam <= n; ++lam) {
                 const int M = 1 << (n - lam);
                 const bool is_g = (lam == lam_top) && (phi != 0);
-                const float* src = nullptr;
+                const Real* src = nullptr;
                 if (lam > 1) src = xrow(lam - 1, 0) + get_ptr(px, lam - 2);
                 const uint32_t* sw = nullptr;
                 if (is_g && lam < n) sw = srow(lam, 0) + get_ptr(ps, lam - 1);
-                float* dst = (lam < n) ? xrow(lam, 0) + lane : nullptr;
+                Real* dst = (lam < n) ? xrow(lam, 0) + lane : nullptr;
                 if (active) {
                     for (int i = 0; i < M; ++i) {
-                        float x0, x1;
+                        Real x0, x1;
                         int beta = i;
                         if (lam == 1) {
                             // channel layer: reference pairs are (2k, 2k+1); k runs in memory
                             // order, the result lands at the bit-reversed position.
-                            const float2 v = *reinterpret_cast<const float2*>(chan + 2 * i);
-                            x0 = v.x; x1 = v.y;
+                            x0 = chan[2 * i]; x1 = chan[2 * i + 1];
                             beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
                         } else {
                             x0 = src[(size_t)i << 5];
                             x1 = src[(size_t)(i + M) << 5];
                         }
-                        float y;
+                        Real y;
                         if (is_g) {
                             uint32_t bit;
                             if (lam == n) bit = s_n & 1u;
                             else bit = (sw[(size_t)(beta >> 5) << 5] >> (beta & 31)) & 1u;
                             y = x1 + (bit ? -x0 : x0);                      // PolarCode.cpp:448-451
                         } else {
-                            y = f_rule(x0, x1);                              // PolarCode.cpp:438-446
+                            y = Arith<Real>::f(x0, x1);                              // PolarCode.cpp:438-446
                         }
                         if (lam == n) lam_n = y; else dst[(size_t)beta << 5] = y;
                     }
@@ -229,11 +255,11 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
             uint32_t u = 0;
             if (frozen) {
                 // PolarCode.cpp:475-487
-                if (active) pm += softplus_ref(-lam_n);
+                if (active) pm += Arith<Real>::softplus(-lam_n);
             } else {
                 // PolarCode.cpp:489-607. Metrics are kept positive (m = -probForks).
-                const float m0 = pm + softplus_ref(-lam_n);
-                const float m1 = pm + softplus_ref(lam_n);
+                const Real m0 = pm + Arith<Real>::softplus(-lam_n);
+                const Real m1 = pm + Arith<Real>::softplus(lam_n);
                 const unsigned act_all = __ballot_sync(FULL_MASK, active);
                 const unsigned act_g = (act_all >> gbase) & gmask_lo;
                 const int A = __popc(act_g);
@@ -245,9 +271,9 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
                 }
                 if (__any_sync(FULL_MASK, need_select)) {
                     // fast exit: every likely fork strictly beats every unlikely fork, list is full
-                    const float lo = fminf(m0, m1), hi = fmaxf(m0, m1);
-                    const float worst_likely = group_max(active ? lo : -CUDART_INF_F, W);
-                    const float best_unlikely = group_min(active ? hi : CUDART_INF_F, W);
+                    const Real lo = rmin<Real>(m0, m1), hi = rmax<Real>(m0, m1);
+                    const Real worst_likely = group_max<Real>(active ? lo : -Arith<Real>::inf(), W);
+                    const Real best_unlikely = group_min<Real>(active ? hi : Arith<Real>::inf(), W);
                     if (need_select && A == L && best_unlikely > worst_likely) {
                         slow = false;
                         keep0 = (m0 <= m1);      // m0 == m1 cannot happen here (would not be strict)
@@ -258,8 +284,8 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
                         // == PolarCode.cpp:528-553 (sort, threshold, '>' pass then '==' pass in index order).
                         int r0 = 0, r1 = 0;
                         for (int j = 0; j < W; ++j) {
-                            const float o0 = __shfl_sync(FULL_MASK, m0, gbase + j);
-                            const float o1 = __shfl_sync(FULL_MASK, m1, gbase + j);
+                            const Real o0 = __shfl_sync(FULL_MASK, m0, gbase + j);
+                            const Real o1 = __shfl_sync(FULL_MASK, m1, gbase + j);
                             const bool oa = (act_g >> j) & 1u;
                             if (oa) {
                                 // other fork indices 2j, 2j+1; mine 2*slot, 2*slot+1
@@ -300,14 +326,14 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
                     const int src_lane = srcof[lane];
                     __syncwarp();
                     const bool is_new = (src_lane != lane);
-                    const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
+                    const Real src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
                     const unsigned long long src_px = __shfl_sync(FULL_MASK, px, src_lane);
                     const unsigned long long src_ps = __shfl_sync(FULL_MASK, ps, src_lane);
                     const uint32_t src_sn = __shfl_sync(FULL_MASK, s_n, src_lane);
                     if (is_new) {
                         active = true; pm = src_m1; u = 1u; px = src_px; ps = src_ps; s_n = src_sn;
                     } else if (kill) {
-                        active = false; pm = 0.0f;
+                        active = false; pm = 0;
                     } else if (active) {
                         u = keep0 ? 0u : 1u;
                         pm = keep0 ? m0 : m1;
@@ -378,8 +404,8 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgs a) {
         const unsigned pass_all = __ballot_sync(FULL_MASK, active && pass);
         const unsigned pass_g = (pass_all >> gbase) & gmask_lo;
         const bool use_parity = (a.crc != 0) && (pass_g != 0);
-        const bool eligible = active && (use_parity ? pass : true) && (pm < CUDART_INF_F);
-        const float best = group_min(eligible ? pm : CUDART_INF_F, W);
+        const bool eligible = active && (use_parity ? pass : true) && (pm < Arith<Real>::inf());
+        const Real best = group_min<Real>(eligible ? pm : Arith<Real>::inf(), W);
         const unsigned cand_all = __ballot_sync(FULL_MASK, eligible && pm == best);
         const unsigned cand_g = (cand_all >> gbase) & gmask_lo;
         const int win_slot = cand_g ? (__ffs(cand_g) - 1) : 0;
@@ -568,7 +594,9 @@ struct polar_b200_ctx {
     uint16_t* d_inv_order = nullptr;       // synth: decoding position -> info / parity index
     uint32_t* d_crc_rows = nullptr;        // synth: parity matrix rows packed over the info index
     float* d_amp = nullptr;                // synth: per-Eb/N0 amplitudes (up to 64)
-    float* d_gx = nullptr;
+    void* d_gx = nullptr;                  // generic-kernel LLR scratch (float or double rows)
+    int scratch_elem = 4;
+    double* d_llr64_stage = nullptr;       // host entry point of the f64 mode
     uint32_t* d_gs = nullptr;
     size_t gx_stride = 0, gs_stride = 0;   // per warp, elements
     int scratch_warps = 0;
@@ -606,7 +634,8 @@ struct LaunchPlan {
 
 // Decide which layers live in shared memory. Layers lamS..n-1 of the LLR tree
 // (2^(n-lamS+1) - 2 rows) and the partial-sum layers >= max(lamS,1) go to shared memory.
-LaunchPlan make_plan(const polar_b200_ctx* c) {
+LaunchPlan make_plan(const polar_b200_ctx* c, int elem = 4) {
+    const int rowb = 32 * elem;                       // bytes of one LLR row
     LaunchPlan p;
     memset(&p, 0, sizeof(p));
     const int n = c->n;
@@ -626,7 +655,7 @@ LaunchPlan make_plan(const polar_b200_ctx* c) {
             int xr = (1 << (n - cand + 1)) - 2;
             int sr = 0;
             for (int lam = (cand < 1 ? 1 : cand); lam <= n - 1; ++lam) sr += ((1 << (n - lam)) + 31) / 32;
-            if ((xr + sr) * 128 + 32 > budget_per_warp) break;
+            if (xr * rowb + sr * 128 + 32 > budget_per_warp) break;
             lamS = cand;
         }
     }
@@ -640,23 +669,24 @@ LaunchPlan make_plan(const polar_b200_ctx* c) {
     for (int lam = lamSS; lam <= n - 1; ++lam) { p.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
     p.smem_s_rows = off;
     p.gx_rows = (size_t)(1 << n) - ((size_t)1 << (n - lamS + 1));
-    p.smem_bytes = ((p.smem_x_rows + p.smem_s_rows) * 128 + 32) * p.wpb;
+    p.smem_bytes = (p.smem_x_rows * rowb + p.smem_s_rows * 128 + 32) * p.wpb;
     return p;
 }
 
-int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p) {
+int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p, int elem = 4) {
     const int warps = p.blocks * p.wpb;
-    if (c->d_gx && c->scratch_warps >= warps && c->scratch_lamS == p.lamS) return 0;
+    if (c->d_gx && c->scratch_warps >= warps && c->scratch_lamS == p.lamS && c->scratch_elem == elem) return 0;
     if (c->d_gx) cudaFree(c->d_gx);
     if (c->d_gs) cudaFree(c->d_gs);
     c->d_gx = nullptr; c->d_gs = nullptr;
     c->gx_stride = (p.gx_rows ? p.gx_rows : 1) * 32;
     c->gs_stride = (p.gs_rows ? p.gs_rows : 1) * 32;
-    CU_TRY(cudaMalloc(&c->d_gx, c->gx_stride * warps * sizeof(float)));
+    CU_TRY(cudaMalloc(&c->d_gx, c->gx_stride * warps * elem));
     CU_TRY(cudaMalloc(&c->d_gs, c->gs_stride * warps * sizeof(uint32_t)));
     c->scratch_warps = warps;
     c->scratch_lamS = p.lamS;
-    c->scratch_bytes = (c->gx_stride * sizeof(float) + c->gs_stride * sizeof(uint32_t)) * warps;
+    c->scratch_elem = elem;
+    c->scratch_bytes = (c->gx_stride * elem + c->gs_stride * sizeof(uint32_t)) * warps;
     return 0;
 }
 
@@ -717,6 +747,34 @@ int pick_fast_variant(int n, int L) {
     for (int i = 0; i < kNumFastVariants; ++i)
         if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog) return i;
     return -1;
+}
+
+template <class Real>
+int decode_generic(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
+    LaunchPlan p = make_plan(c, (int)sizeof(Real));
+    int rc = ensure_scratch(c, p, (int)sizeof(Real));
+    if (rc) return rc;
+    DecodeArgsT<Real> a;
+    memset(&a, 0, sizeof(a));
+    a.llr = llr; a.out = info_packed;
+    a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.gx = static_cast<Real*>(c->d_gx); a.gs = c->d_gs; a.gx_stride = c->gx_stride; a.gs_stride = c->gs_stride;
+    a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.L = L;
+    int W = 1; while (W < L) W <<= 1;
+    a.W = W; a.lamS = p.lamS; a.smem_x_rows = p.smem_x_rows; a.smem_s_rows = p.smem_s_rows;
+    memcpy(a.s_off, p.s_off, sizeof(a.s_off));
+    const int G = 32 / W;
+    const int groups = (B + G - 1) / G;
+    int blocks = p.blocks;
+    const int need_blocks = (groups + p.wpb - 1) / p.wpb;
+    if (blocks > need_blocks) blocks = need_blocks;
+    CU_TRY(cudaFuncSetAttribute(scl_decode_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    scl_decode_kernel<Real><<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes;
+    c->last_kernel = sizeof(Real) == 8 ? -1 : 0;
+    return POLAR_B200_OK;
 }
 
 int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st) {
@@ -882,7 +940,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
     cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
-    cudaFree(c->d_fgx); cudaFree(c->d_fgs);
+    cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage);
     if (c->st_h2d) {
         cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_run); cudaStreamDestroy(c->st_d2h);
         for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
@@ -900,29 +958,7 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int fv = pick_fast_variant(c->n, L);
     if (fv >= 0) return decode_fast(c, fv, llr, B, L, info_packed, st);
-    LaunchPlan p = make_plan(c);
-    int rc = ensure_scratch(c, p);
-    if (rc) return rc;
-    DecodeArgs a;
-    memset(&a, 0, sizeof(a));
-    a.llr = llr; a.out = info_packed;
-    a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
-    a.gx = c->d_gx; a.gs = c->d_gs; a.gx_stride = c->gx_stride; a.gs_stride = c->gs_stride;
-    a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.L = L;
-    int W = 1; while (W < L) W <<= 1;
-    a.W = W; a.lamS = p.lamS; a.smem_x_rows = p.smem_x_rows; a.smem_s_rows = p.smem_s_rows;
-    memcpy(a.s_off, p.s_off, sizeof(a.s_off));
-    const int G = 32 / W;
-    const int groups = (B + G - 1) / G;
-    int blocks = p.blocks;
-    const int need_blocks = (groups + p.wpb - 1) / p.wpb;
-    if (blocks > need_blocks) blocks = need_blocks;
-    CU_TRY(cudaFuncSetAttribute(scl_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    scl_decode_kernel<<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes; c->last_kernel = 0;
-    return POLAR_B200_OK;
+    return decode_generic<float>(c, llr, B, L, info_packed, st);
 }
 
 int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int B, int L,
@@ -950,7 +986,7 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
         if (fv >= 0) {
             per_round = c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);
         } else {
-            LaunchPlan p = make_plan(c);
+            LaunchPlan p = make_plan(c, 4);
             int W = 1; while (W < L) W <<= 1;
             per_round = p.blocks * p.wpb * (32 / W);
         }
@@ -980,6 +1016,32 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
                                cudaMemcpyDeviceToHost, c->st_d2h));
     }
     CU_TRY(cudaStreamSynchronize(c->st_d2h));
+    return POLAR_B200_OK;
+}
+
+int polar_b200_decode_scl_llr_f64(polar_b200_ctx* c, const double* llr, int B, int L,
+                                  uint32_t* info_packed, void* cuda_stream) {
+    if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
+    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    return decode_generic<double>(c, llr, B, L, info_packed, (cudaStream_t)cuda_stream);
+}
+
+int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* c, const double* llr_host, int B, int L,
+                                       uint32_t* info_packed_host, void* cuda_stream) {
+    if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
+    if (B > c->max_batch) return POLAR_B200_E_BATCH;
+    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (!c->d_llr64_stage) CU_TRY(cudaMalloc(&c->d_llr64_stage, (size_t)c->max_batch * c->N * sizeof(double)));
+    CU_TRY(cudaMemcpyAsync(c->d_llr64_stage, llr_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = decode_generic<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
     return POLAR_B200_OK;
 }
 

@@ -284,3 +284,42 @@ def test_device_bler_sweep_agrees_with_host_sweep(torch_cuda):
     p1, p2 = dev[..., 0] / total, host[..., 0] / total
     sigma = np.sqrt((p1 * (1 - p1) + p2 * (1 - p2)) / total) + 1e-4
     assert np.all(np.abs(p1 - p2) <= 5 * sigma)
+
+
+def test_reference_precision_mode(torch_cuda):
+    """f64 mode: double LLRs, the reference's literal formulas in double on the GPU. Equals the double
+    oracle on AWGN batches, on the lattice edge rows that fp32 cannot reproduce, and makes the BLER
+    harness table identical to the oracle harness even at low Eb/N0 without parity bits."""
+    from polar_b200 import PolarCode
+    for (n, K, crc, L, B, eb) in [(9, 256, 16, 8, 128, 1.0), (11, 1024, 0, 4, 48, 1.0), (11, 1024, 16, 32, 24, 1.25),
+                                  (7, 64, 8, 3, 100, 0.5), (5, 16, 4, 16, 64, 0.0)]:
+        port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+        _, llr = awgn_llrs(port, B, eb, seed=77 + n + L)
+        want = port.decode_batch(llr, L, nthreads=os.cpu_count() or 1)
+        assert np.array_equal(pc.decode_batch_f64(llr.astype(np.float64), L), want)
+    for (n, K, crc) in [(9, 256, 16), (7, 64, 8)]:
+        e = load_edge(n, K, crc)
+        pc = PolarCode(n, K, 0.32, crc)
+        for L in (1, 2, 4, 32):
+            got = pc.decode_batch_f64(e["llr"].astype(np.float64), L)
+            bad = [i for i in range(len(got)) if not np.array_equal(got[i], e[L][i])]
+            # in double with the literal formulas even the lattice rows (exact cancellations resolved by the
+            # last-bit rounding of exp/log) come out as in the reference
+            assert bad == [], "f64 mode, edge rows differing (n=%d L=%d): %s" % (n, L, bad)
+    ebno, lists = [0.0, 1.0, 2.0], [1, 4, 32]
+    want, _ = Port(8, 128, 0.32, 0).get_bler_quick(ebno, lists, max_err=30, max_runs=200)
+    pc = PolarCode(8, 128, 0.32, 0)
+    pc.set_exact(True)
+    assert np.array_equal(pc.get_bler_quick(ebno, lists, max_err=30, max_runs=200), want)
+
+
+def test_unmodified_reference_main_in_reference_precision(torch_cuda):
+    """POLAR_B200_EXACT=1: the unmodified main.cpp through the drop-in class prints the reference's table."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "polar_b200_main")
+    if not os.path.exists(exe):
+        pytest.skip("acceptance binary not prebuilt (needs /root/reference at build time)")
+    env = dict(os.environ, POLAR_B200_EXACT="1")
+    txt = subprocess.run([exe], capture_output=True, text=True, check=True, timeout=900, env=env).stdout
+    rows = [ln for ln in txt.splitlines() if ln.strip() and not ln.startswith("Running iteration")]
+    want = [w for w in open(os.path.join(GOLDEN, "ref_main_table.txt")).read().splitlines() if w.strip()]
+    assert rows == want
