@@ -458,6 +458,7 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
     constexpr int T = C::T, NLOG = C::NLOG, LB = C::LB;
     const int lam_top = (phi0 == 0) ? 0 : NLOG - (__ffs(phi0) - 1);      // <= LB
     bool first = true;
+    __syncwarp();       // every lane is done reading the columns that are about to be overwritten
     if (lam_top <= T) {
         const int node = phi0 >> (NLOG - T);
         switch (node) {
@@ -631,6 +632,7 @@ __device__ __noinline__ unsigned long long deep_chain(uint32_t* gs, uint32_t* ss
     int lam = NLOG - 5;
     uint32_t* D = sbase_rt<C>(w, lam_end) + lane;
     const int Wd = 1 << (t - 5);
+    __syncwarp();       // every lane is done reading the columns that are about to be overwritten
     D[(Wd - 1) * 32] = P;
     for (; lam > lam_end; --lam) {
         const int mw = 1 << (NLOG - lam - 5);

@@ -1,0 +1,19 @@
+"""Small decodes through every kernel family, for compute-sanitizer (memcheck / racecheck)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np
+from oracle_lib import Port, awgn_llrs
+from polar_b200 import PolarCode
+ok = True
+for (n,K,crc,L,B) in [(9,256,16,32,6),(9,256,16,4,19),(9,256,0,16,5),(11,1024,16,32,3),(11,1024,16,8,9),(7,64,8,3,21),(9,256,0,1,40),(8,128,8,32,4)]:
+    port = Port(n,K,0.32,crc); pc = PolarCode(n,K,0.32,crc)
+    info, llr = awgn_llrs(port, B, 1.5, 5)
+    want = port.decode_batch(llr, L)
+    got = pc.decode_batch(llr, L)
+    g64 = pc.decode_batch_f64(llr.astype(np.float64), L)
+    l2, t2 = pc.synthesize(8, [2.0], 3)
+    same = np.array_equal(got, want) and np.array_equal(g64, want)
+    ok &= same
+    print(n, K, crc, L, B, "kernel kind", pc.info(6), "ok" if same else "MISMATCH", flush=True)
+print("ALL OK" if ok else "FAIL")
