@@ -718,21 +718,36 @@ cudaError_t prepare_fast() {
       fast::Cfg<NLOG, T, LAMS, WLOG>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS>,               \
       prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS> }
 
+#define POLAR_FAST_SG(NLOG, T, LAMS, WLOG, SG, WPB, BPS)                                                              \
+    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG, SG>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG, SG>::GS_WORDS, \
+      fast::Cfg<NLOG, T, LAMS, WLOG, SG>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG>, WPB, BPS>,               \
+      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG>, WPB, BPS> }
+
+#define POLAR_FAST_TM(NLOG, T, LAMS, WLOG, WPB, BPS)                                                                \
+    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::GS_WORDS, \
+      fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS>,               \
+      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS> }
+
 // (log2 N, virtual top layers, first shared-memory layer, log2 lanes per codeword, warps/block, blocks/SM).
 // pick_fast_variant() takes the first entry matching (n, lanes); POLAR_B200_FAST_VARIANT=<index> overrides.
 const FastVariant kFastVariants[] = {
-    POLAR_FAST(11, 3, 5, 5, 4, 4),   // 0: N=2048, lists 17..32: layers 3-4 in HBM scratch, 5-6 shared, 16 warps/SM
-    POLAR_FAST(11, 3, 6, 5, 4, 5),   // 1: N=2048, lists 17..32: layers 3-5 in HBM scratch, 20 warps/SM
-    POLAR_FAST(11, 3, 5, 4, 4, 4),   // 2: N=2048, lists 9..16 (2 codewords per warp)
-    POLAR_FAST(11, 3, 5, 3, 4, 4),   // 3: N=2048, lists 5..8  (4 codewords per warp)
-    POLAR_FAST(11, 3, 5, 2, 4, 4),   // 4: N=2048, lists 3..4  (8 codewords per warp)
-    POLAR_FAST(9, 3, 4, 5, 4, 5),    // 5: N=512, lists 17..32: layer 3 in HBM scratch, 20 warps/SM
-    POLAR_FAST(9, 3, 4, 4, 4, 5),    // 6: N=512, lists 9..16
-    POLAR_FAST(9, 3, 4, 3, 4, 5),    // 7: N=512, lists 5..8
-    POLAR_FAST(9, 3, 4, 2, 4, 5),    // 8: N=512, lists 3..4
-    POLAR_FAST(10, 3, 4, 5, 4, 4),   // 9: N=1024, lists 17..32
-    POLAR_FAST(12, 3, 6, 5, 4, 4),   // 10: N=4096, lists 17..32
-    POLAR_FAST(8, 3, 3, 5, 4, 4),    // 11: N=256, lists 17..32
+    // N=2048: layer 3 in the HBM/L2 scratch, layer 4 in tensor memory, layers 5-6 shared, 7-11 registers; 16 warps/SM
+    POLAR_FAST_TM(11, 3, 5, 5, 4, 4),  // 0: lists 17..32
+    POLAR_FAST_TM(11, 3, 5, 4, 4, 4),  // 1: lists 9..16 (2 codewords per warp)
+    POLAR_FAST_TM(11, 3, 5, 3, 4, 4),  // 2: lists 5..8  (4 codewords per warp)
+    POLAR_FAST_TM(11, 3, 5, 2, 4, 4),  // 3: lists 3..4  (8 codewords per warp)
+    // N=512: layer 3 in the scratch, layer 4 shared, 20 warps/SM
+    POLAR_FAST(9, 3, 4, 5, 4, 5),      // 4: lists 17..32
+    POLAR_FAST(9, 3, 4, 4, 4, 5),      // 5: lists 9..16
+    POLAR_FAST(9, 3, 4, 3, 4, 5),      // 6: lists 5..8
+    POLAR_FAST(9, 3, 4, 2, 4, 5),      // 7: lists 3..4
+    // other block lengths, lists 17..32
+    POLAR_FAST_TM(10, 3, 5, 5, 4, 4),  // 8: N=1024: layer 3 scratch, layer 4 tensor memory, layer 5 shared
+    POLAR_FAST_TM(12, 3, 6, 5, 4, 4),  // 9: N=4096: layers 3-4 scratch, layer 5 tensor memory, layers 6-7 shared
+    POLAR_FAST(8, 3, 3, 5, 4, 4),      // 10: N=256
+    // alternates without tensor memory (POLAR_B200_FAST_VARIANT=<index>)
+    POLAR_FAST(11, 3, 5, 5, 4, 4),     // 11: N=2048 lists 17..32, layers 3-4 in the scratch
+    POLAR_FAST(11, 3, 6, 5, 4, 5),     // 12: N=2048 lists 17..32, layers 3-5 in the scratch, 20 warps/SM
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 

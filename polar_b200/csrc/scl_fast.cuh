@@ -28,7 +28,7 @@
 
 namespace fast {
 
-template <int NLOG_, int T_, int LAMS_, int WLOG_ = 5>
+template <int NLOG_, int T_, int LAMS_, int WLOG_ = 5, int SGMIN_ = 16, int TM_ = 0>
 struct Cfg {
     static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_, WLOG = WLOG_;
     static constexpr int W = 1 << WLOG;               // lanes per codeword (list size rounded up to a power of two)
@@ -42,14 +42,21 @@ struct Cfg {
     static_assert(LAMS >= T && LAMS <= LB, "bad shared-memory split");
     // rows of per-path layers [a, b)
     static constexpr __host__ __device__ int rows(int a, int b) { return (N >> (a - 1)) - (N >> (b - 1)); }
-    static constexpr int GX_ROWS = rows(T, LAMS);      // HBM scratch rows (32 floats each)
+    // TM: the last layer below the shared-memory ones (LT = LAMS-1) lives in tensor memory (TMEM), used as a
+    // per-warp scratch: one 32-lane quadrant x (N >> LT) columns = that layer's [beta][lane] rows.
+    static constexpr bool TM = TM_ != 0;
+    static constexpr int LT = LAMS - 1;
+    static constexpr int TM_COLS = TM ? ((N >> LT) < 32 ? 32 : (N >> LT)) : 0;
+    static_assert(!TM || (LT > T && (N >> LT) <= 128), "TMEM layer must lie strictly between T and LAMS and have <= 128 rows");
+    static constexpr int GX_ROWS = rows(T, TM ? LT : LAMS);   // HBM scratch rows (32 floats each)
     static constexpr int SX_ROWS = rows(LAMS, LB);     // shared rows (layers LAMS..NLOG-5)
     static constexpr int XS_FLOATS = N - MT;           // shared compact arrays XS_1..XS_T
     static constexpr __host__ __device__ int xs_off(int lev) { return N - (N >> (lev - 1)); }   // XS_lev at this float offset
     // partial-sum word layers: 1..NLOG-5 (>= 32 bits). Layers with >= 16 words live in HBM scratch.
     static constexpr int SWL = NLOG - 5;               // last word layer
     static constexpr __host__ __device__ int swords(int lam) { return (N >> lam) / 32; }
-    static constexpr __host__ __device__ bool s_global(int lam) { return lam == 0 || swords(lam) >= 16; }
+    // partial-sum word layers with at least SGMIN words live in the HBM scratch, smaller ones in shared memory
+    static constexpr __host__ __device__ bool s_global(int lam) { return lam == 0 || swords(lam) >= SGMIN_; }
     static constexpr __host__ __device__ int s_off(int lam) {              // row offset within its space
         int off = 0;
         for (int j = 0; j < lam; ++j)
@@ -87,6 +94,7 @@ struct Warp {          // per-warp pointers
     float* xs;         // compact shared arrays of THIS LANE's codeword
     uint32_t* gs;      // HBM partial-sum rows
     const float* chan; // channel LLRs of THIS LANE's codeword
+    uint32_t tm;       // TMEM address of this warp's quadrant (TM configurations)
     int lane;
 };
 
@@ -136,6 +144,22 @@ template <class P> __device__ __forceinline__ P* shfl_ptr(P* p, int src) {
     return reinterpret_cast<P*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(p), src));
 }
 
+// ---- tensor memory as a per-warp scratch (tcgen05.ld/st, shape 32x32b: lane i of the warp <-> TMEM lane i of
+// the warp's quadrant, one 32-bit value per column) ----
+__device__ __forceinline__ void tm_st4(uint32_t taddr, const float (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+                 :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+                    "r"(__float_as_uint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tm_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r0, r1, r2, r3;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r0); v[1] = __uint_as_float(r1); v[2] = __uint_as_float(r2); v[3] = __uint_as_float(r3);
+}
+__device__ __forceinline__ void tm_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tm_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
 template <class C, int LAM>
 __device__ __forceinline__ float* xbase(const Warp& w) {
     if constexpr (LAM >= C::LAMS) return w.sx + C::rows(C::LAMS, LAM) * 32;
@@ -158,7 +182,7 @@ __device__ __forceinline__ uint32_t* sbase_rt(const Warp& w, int lam) {
 template <class C>
 __device__ __forceinline__ float* xbase_rt(const Warp& w, int lam) {
     float* p = nullptr;
-#define POLAR_XB(L_) if constexpr (L_ >= C::T && L_ < C::LB) { if (lam == L_) p = xbase<C, L_>(w); }
+#define POLAR_XB(L_) if constexpr (L_ >= C::T && L_ < C::LB && !(C::TM && L_ == C::LT)) { if (lam == L_) p = xbase<C, L_>(w); }
     POLAR_XB(2) POLAR_XB(3) POLAR_XB(4) POLAR_XB(5) POLAR_XB(6) POLAR_XB(7) POLAR_XB(8) POLAR_XB(9)
 #undef POLAR_XB
     return p;
@@ -174,7 +198,50 @@ template <class C, int LAM, bool ISG>
 __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
     constexpr int M = C::N >> LAM;
     static_assert(M >= 32, "memory layers have at least 32 rows");
-    const float* src = xbase<C, LAM - 1>(w) + get_ptr(s.px, LAM - 1 - C::T);
+    constexpr bool SRC_TM = C::TM && (LAM - 1 == C::LT), DST_TM = C::TM && (LAM == C::LT);
+    const int pcol = get_ptr(s.px, LAM - 1 - C::T);
+    if constexpr (SRC_TM || DST_TM) {
+        // tcgen05.ld/st are warp-collective: every lane runs the loop (idle lanes work on don't-care data)
+        const uint32_t* sw = nullptr;
+        if constexpr (ISG) sw = sbase<C, LAM>(w) + get_ptr(s.ps, LAM - 1);
+        const float* src = nullptr;
+        if constexpr (!SRC_TM) src = xbase<C, LAM - 1>(w) + pcol;
+        float* dst = nullptr;
+        if constexpr (!DST_TM) dst = xbase<C, LAM>(w) + w.lane;
+        uint32_t word = 0;
+#pragma unroll 1
+        for (int i0 = 0; i0 < M; i0 += 4) {
+            if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+            float a[4], b[4], y[4];
+            if constexpr (SRC_TM) {
+                tm_ld4(w.tm + i0, a);
+                tm_ld4(w.tm + i0 + M, b);
+                tm_wait_ld();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {             // the path's rows may belong to another lane's column
+                    a[j] = __shfl_sync(FULL_MASK, a[j], pcol);
+                    b[j] = __shfl_sync(FULL_MASK, b[j], pcol);
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a[j] = src[(i0 + j) * 32]; b[j] = src[(i0 + j + M) * 32]; }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if constexpr (ISG) y[j] = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
+                else y[j] = f_rule(a[j], b[j]);
+            }
+            if constexpr (DST_TM) tm_st4(w.tm + i0, y);
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[(i0 + j) * 32] = y[j];
+            }
+        }
+        if constexpr (DST_TM) tm_wait_st();
+        s.px = set_ptr(s.px, LAM - C::T, w.lane);
+        return;
+    }
+    const float* src = xbase<C, LAM - 1>(w) + pcol;
     if (s.active) {
         float* dst = xbase<C, LAM>(w) + w.lane;
         const uint32_t* sw = nullptr;
@@ -437,7 +504,14 @@ __device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
             for (int b = lane; b < half; b += 32) nxt[b] = f_rule(cur[b], cur[b + half]);
         }
         __syncwarp();
-        if (lam + 1 < LB) {
+        if (C::TM && lam + 1 == C::LT) {
+            // publish into the tensor-memory layer: every lane stores the same rows (only column c0 matters)
+            for (int b = 0; b < half; b += 4) {
+                const float v[4] = {nxt[b], nxt[b + 1], nxt[b + 2], nxt[b + 3]};
+                tm_st4(w.tm + b, v);
+            }
+            tm_wait_st();
+        } else if (lam + 1 < LB) {
             float* col = xbase_rt<C>(w, lam + 1) + c0;
             for (int b = lane; b < half; b += 32) col[b * 32] = nxt[b];
         }
@@ -683,6 +757,20 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     w.srcof = my + (C::SX_ROWS + C::SS_ROWS) * 128;
     w.stack = w.srcof + 32;
     constexpr int W = C::W, G = C::G;
+    w.tm = 0;
+    if constexpr (C::TM) {
+        static_assert(WPB == 4, "one warp per TMEM lane quadrant");
+        __shared__ uint32_t tm_base;
+        if (wib == 0) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(&tm_base)), "r"((uint32_t)C::TM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        w.tm = tm_base + ((uint32_t)(wib * 32) << 16);
+    }
     const int gbase = lane & ~(W - 1), slot = lane & (W - 1), grp_in_warp = lane / W;
     w.gx = a.gx + C::GX_FLOATS * gwarp;
     w.xs = w.gx + (size_t)C::GX_ROWS * 32 + (size_t)grp_in_warp * C::XS_FLOATS;
@@ -812,6 +900,13 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             }
         }
         __syncwarp();
+    }
+    if constexpr (C::TM) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (wib == 0)
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
+                         :: "r"(w.tm & 0x0000FFFFu), "r"((uint32_t)C::TM_COLS) : "memory");
     }
 }
 
