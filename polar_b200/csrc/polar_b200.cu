@@ -736,11 +736,11 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST_TM(11, 3, 5, 4, 4, 4),  // 1: lists 9..16 (2 codewords per warp)
     POLAR_FAST_TM(11, 3, 5, 3, 4, 4),  // 2: lists 5..8  (4 codewords per warp)
     POLAR_FAST_TM(11, 3, 5, 2, 4, 4),  // 3: lists 3..4  (8 codewords per warp)
-    // N=512: layer 3 in the scratch, layer 4 shared, 20 warps/SM
-    POLAR_FAST(9, 3, 4, 5, 4, 5),      // 4: lists 17..32
-    POLAR_FAST(9, 3, 4, 4, 4, 5),      // 5: lists 9..16
-    POLAR_FAST(9, 3, 4, 3, 4, 5),      // 6: lists 5..8
-    POLAR_FAST(9, 3, 4, 2, 4, 5),      // 7: lists 3..4
+    // N=512: nothing per path leaves the SM: layer 3 in tensor memory, layer 4 shared, 5-9 registers; 20 warps/SM
+    POLAR_FAST_TM(9, 3, 4, 5, 4, 5),   // 4: lists 17..32
+    POLAR_FAST_TM(9, 3, 4, 4, 4, 5),   // 5: lists 9..16
+    POLAR_FAST_TM(9, 3, 4, 3, 4, 5),   // 6: lists 5..8
+    POLAR_FAST_TM(9, 3, 4, 2, 4, 5),   // 7: lists 3..4
     // other block lengths, lists 17..32
     POLAR_FAST_TM(10, 3, 5, 5, 4, 4),  // 8: N=1024: layer 3 scratch, layer 4 tensor memory, layer 5 shared
     POLAR_FAST_TM(12, 3, 6, 5, 4, 4),  // 9: N=4096: layers 3-4 scratch, layer 5 tensor memory, layers 6-7 shared
@@ -748,6 +748,7 @@ const FastVariant kFastVariants[] = {
     // alternates without tensor memory (POLAR_B200_FAST_VARIANT=<index>)
     POLAR_FAST(11, 3, 5, 5, 4, 4),     // 11: N=2048 lists 17..32, layers 3-4 in the scratch
     POLAR_FAST(11, 3, 6, 5, 4, 5),     // 12: N=2048 lists 17..32, layers 3-5 in the scratch, 20 warps/SM
+    POLAR_FAST(9, 3, 4, 5, 4, 5),      // 13: N=512 lists 17..32, layer 3 in the scratch
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 

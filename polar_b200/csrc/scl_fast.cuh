@@ -47,7 +47,7 @@ struct Cfg {
     static constexpr bool TM = TM_ != 0;
     static constexpr int LT = LAMS - 1;
     static constexpr int TM_COLS = TM ? ((N >> LT) < 32 ? 32 : (N >> LT)) : 0;
-    static_assert(!TM || (LT > T && (N >> LT) <= 128), "TMEM layer must lie strictly between T and LAMS and have <= 128 rows");
+    static_assert(!TM || (LT >= T && (N >> LT) <= 128), "TMEM layer must lie in [T, LAMS) and have <= 128 rows");
     static constexpr int GX_ROWS = rows(T, TM ? LT : LAMS);   // HBM scratch rows (32 floats each)
     static constexpr int SX_ROWS = rows(LAMS, LB);     // shared rows (layers LAMS..NLOG-5)
     static constexpr int XS_FLOATS = N - MT;           // shared compact arrays XS_1..XS_T
@@ -150,6 +150,9 @@ __device__ __forceinline__ void tm_st4(uint32_t taddr, const float (&v)[4]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                  :: "r"(taddr), "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
                     "r"(__float_as_uint(v[3])) : "memory");
+}
+__device__ __forceinline__ void tm_st1(uint32_t taddr, float v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" :: "r"(taddr), "r"(__float_as_uint(v)) : "memory");
 }
 __device__ __forceinline__ void tm_ld4(uint32_t taddr, float (&v)[4]) {
     uint32_t r0, r1, r2, r3;
@@ -360,8 +363,10 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
     constexpr int T = C::T, MT = C::MT, NLOG = C::NLOG;
     constexpr int S0 = lead_zeros(NODE, T);          // values enter at level S0 (0 = channel)
     constexpr int CNT = 1 << (T - S0);
-    float* dst = xbase<C, T>(w) + w.lane;
-    if (s.active) {
+    constexpr bool DST_TM = C::TM && (C::LT == T);     // layer T itself lives in tensor memory
+    float* dst = nullptr;
+    if constexpr (!DST_TM) dst = xbase<C, T>(w) + w.lane;
+    if (DST_TM || s.active) {                           // tcgen05.st is warp-collective
 #pragma unroll 1
         for (int wd = 0; wd < MT / 32; ++wd) {
             // partial-sum words of this path for the g levels: level lev, local element i sits at
@@ -411,9 +416,11 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                         else v[i] = f_rule(v[2 * i], v[2 * i + 1]);
                     });
                 });
-                dst[beta * 32] = v[0];
+                if constexpr (DST_TM) tm_st1(w.tm + beta, v[0]);
+                else dst[beta * 32] = v[0];
             }
         }
+        if constexpr (DST_TM) tm_wait_st();
     }
     s.px = set_ptr(s.px, 0, w.lane);
 }
@@ -436,10 +443,24 @@ __device__ __forceinline__ void top_solo_one(const Warp& w, const float* chan, f
         for (int b = w.lane; b < M; b += 32) out[b] = f_rule(in[b], in[b + M]);
         __syncwarp();
     }
-    const float* xt = xs + C::xs_off(T);
-    float* col = xbase<C, T>(w) + c0;
-    for (int b = w.lane; b < C::MT; b += 32) col[b * 32] = xt[b];
-    __syncwarp();
+    if constexpr (!(C::TM && C::LT == T)) {
+        const float* xt = xs + C::xs_off(T);
+        float* col = xbase<C, T>(w) + c0;
+        for (int b = w.lane; b < C::MT; b += 32) col[b * 32] = xt[b];
+        __syncwarp();
+    }
+}
+// layer T in tensor memory: every lane stores its own codeword's XS_T rows into its column
+template <class C>
+__device__ __forceinline__ void top_solo_publish_tm(const Warp& w) {
+    if constexpr (C::TM && C::LT == C::T) {
+        const float* xt = w.xs + C::xs_off(C::T);
+        for (int b = 0; b < C::MT; b += 4) {
+            const float v[4] = {xt[b], xt[b + 1], xt[b + 2], xt[b + 3]};
+            tm_st4(w.tm + b, v);
+        }
+        tm_wait_st();
+    }
 }
 // all codewords of the warp, one after the other (c0 = local index of the first path)
 template <class C>
@@ -451,6 +472,7 @@ __device__ __forceinline__ void top_solo(const Warp& w, int c0, bool valid) {
         const bool ok = __shfl_sync(FULL_MASK, (int)valid, g * C::W);
         if (ok) top_solo_one<C>(w, chan, xs, g * C::W + c0);
     }
+    top_solo_publish_tm<C>(w);
 }
 
 // ---- phase A: the leading PA leaves are frozen and only one path exists, so the warp decodes them
@@ -465,6 +487,7 @@ __device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
     constexpr int T = C::T, LB = C::LB, MT = C::MT, N = C::N;
     const int lane = w.lane;
     top_solo_one<C>(w, w.chan, w.xs, c0);
+    top_solo_publish_tm<C>(w);
     float* bufA = w.xs + C::XS_FLOATS;
     float* bufB = bufA + MT / 2;
     float* V = bufB + MT / 2;
