@@ -11,6 +11,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file
 tail -12 gpurun_out/launches_$tag.csv
 ncu --set full --clock-control none --import-source on -k regex:scl_ -s 3 -c 1 -f -o gpurun_out/prof_$tag python bench.py --steps 1 --warmup 3 --no-cpu --e2e-steps 1 --batch 16384 > gpurun_out/ncu_full_$tag.log 2>&1
 ls -la gpurun_out/
+timeout 300 compute-sanitizer --tool memcheck python tools/sanitize_probe.py 2>&1 | tail -3 > gpurun_out/sanitizer_$tag.txt; timeout 300 compute-sanitizer --tool racecheck python tools/sanitize_probe.py 2>&1 | tail -2 >> gpurun_out/sanitizer_$tag.txt; cat gpurun_out/sanitizer_$tag.txt
 python tools/bler_curve.py $tag 262144 > gpurun_out/bler_curve_$tag.log 2>&1; tail -3 gpurun_out/bler_curve_$tag.log
 python tools/mismatch_rate.py > gpurun_out/mismatch_$tag.txt 2>&1; cat gpurun_out/mismatch_$tag.txt
 oracle/_ref/polar_b200_main | grep -v "^Running" > gpurun_out/main_table_$tag.txt 2>&1; cat gpurun_out/main_table_$tag.txt
