@@ -28,6 +28,12 @@
 
 namespace fast {
 
+// channel LLRs: read-only path. (Streaming / evict-first loads were measured 5% slower: each codeword's
+// LLRs are re-read by four top-layer nodes and those re-reads do hit L2.)
+#ifndef POLAR_LDCHAN
+#define POLAR_LDCHAN(p) __ldg(p)
+#endif
+
 template <int NLOG_, int T_, int LAMS_, int WLOG_ = 5, int SGMIN_ = 16, int TM_ = 0>
 struct Cfg {
     static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_, WLOG = WLOG_;
@@ -387,7 +393,7 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                     const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(beta, NLOG - T));
                     static_for<0, CNT / 4>([&](auto q_c) {
                         constexpr int q = decltype(q_c)::value;
-                        const float4 t4 = __ldg(c4 + q);
+                        const float4 t4 = POLAR_LDCHAN(c4 + q);
                         v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
                     });
                 } else {
@@ -431,7 +437,7 @@ __device__ __forceinline__ void top_solo_one(const Warp& w, const float* chan, f
     constexpr int T = C::T, N = C::N, NLOG = C::NLOG;
     float* xs1 = xs + C::xs_off(1);
     for (int k = w.lane; k < N / 2; k += 32) {
-        const float2 c = __ldg(reinterpret_cast<const float2*>(chan) + k);
+        const float2 c = POLAR_LDCHAN(reinterpret_cast<const float2*>(chan) + k);
         xs1[brev_bits(k, NLOG - 1)] = f_rule(c.x, c.y);
     }
     __syncwarp();
