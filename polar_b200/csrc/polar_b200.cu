@@ -1075,7 +1075,7 @@ int polar_b200_count_errors(polar_b200_ctx* c, const uint32_t* info_packed, cons
 int polar_b200_synthesize(polar_b200_ctx* c, unsigned long long seed, long long first_index, int B,
                           const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed, void* cuda_stream) {
     if (!c || !ebno_db || !llr || !truth_packed || B < 0 || n_ebno < 1 || n_ebno > 64 || first_index < 0) return POLAR_B200_E_ARG;
-    if (c->K > 2048 || c->N > 8192) return POLAR_B200_E_UNSUPPORTED;
+    if (c->K > 2048 || c->N > 8192 || c->crc > 32) return POLAR_B200_E_UNSUPPORTED;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;

@@ -53,6 +53,16 @@ PARITY = [
     (11, 1024, 16, 6, 131, 1.25),
     (11, 1024, 0, 12, 67, 1.25),
     (11, 1024, 16, 24, 65, 1.25),    # 24 paths on 32 lanes
+    (9, 250, 7, 32, 100, 1.5),       # K not a multiple of 32, odd parity-bit count
+    (11, 1000, 11, 4, 99, 1.5),
+    (9, 500, 0, 32, 64, 6.0),        # rate ~ 1: almost nothing frozen
+    (9, 512, 0, 8, 40, 8.0),         # rate 1: no frozen bit at all
+    (9, 8, 0, 32, 64, -6.0),         # very low rate
+    (9, 3, 0, 32, 64, -9.0),         # fewer info bits than log2(L) in the fast kernel: the list never fills
+    (9, 200, 40, 16, 64, 1.0),       # more than 32 parity bits
+    (12, 2048, 16, 32, 10, 1.5),     # N = 4096 (layer 5 in tensor memory)
+    (10, 512, 16, 32, 40, 1.5),      # N = 1024
+    (8, 128, 8, 32, 80, 1.5),        # N = 256
     (12, 2048, 16, 8, 48, 1.5),
     (7, 64, 8, 3, 333, 0.5),         # list size not a power of two, ragged batch
     (6, 20, 3, 5, 257, -1.0),
