@@ -736,11 +736,15 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST_TM(11, 3, 5, 4, 4, 4),  // 1: lists 9..16 (2 codewords per warp)
     POLAR_FAST_TM(11, 3, 5, 3, 4, 4),  // 2: lists 5..8  (4 codewords per warp)
     POLAR_FAST_TM(11, 3, 5, 2, 4, 4),  // 3: lists 3..4  (8 codewords per warp)
+    POLAR_FAST_TM(11, 3, 5, 1, 4, 4),  // list 2 (16 codewords per warp)
+    POLAR_FAST_TM(11, 3, 5, 0, 4, 4),  // list 1 = plain SC (32 codewords per warp, lane = codeword)
     // N=512: nothing per path leaves the SM: layer 3 in tensor memory, layer 4 shared, 5-9 registers; 20 warps/SM
     POLAR_FAST_TM(9, 3, 4, 5, 4, 5),   // 4: lists 17..32
     POLAR_FAST_TM(9, 3, 4, 4, 4, 5),   // 5: lists 9..16
     POLAR_FAST_TM(9, 3, 4, 3, 4, 5),   // 6: lists 5..8
     POLAR_FAST_TM(9, 3, 4, 2, 4, 5),   // 7: lists 3..4
+    POLAR_FAST_TM(9, 3, 4, 1, 4, 5),   // list 2
+    POLAR_FAST_TM(9, 3, 4, 0, 4, 5),   // list 1
     // other block lengths, lists 17..32
     POLAR_FAST_TM(10, 3, 5, 5, 4, 4),  // 8: N=1024: layer 3 scratch, layer 4 tensor memory, layer 5 shared
     POLAR_FAST_TM(12, 3, 6, 5, 4, 4),  // 9: N=4096: layers 3-4 scratch, layer 5 tensor memory, layers 6-7 shared
@@ -754,9 +758,9 @@ constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]
 
 int pick_fast_variant(int n, int L) {
     if (env_int("POLAR_B200_FORCE_GENERIC", 0)) return -1;
-    int wlog = 2;
-    while ((1 << wlog) < L) ++wlog;                 // lanes per codeword; lists 1..2 stay on the generic kernel
-    if (L < 3 || wlog > 5) return -1;
+    int wlog = 0;
+    while ((1 << wlog) < L) ++wlog;                 // lanes per codeword
+    if (L < 1 || wlog > 5) return -1;
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
     if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n && kFastVariants[forced].wlog == wlog)
         return forced;

@@ -39,7 +39,7 @@ struct Cfg {
     static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_, WLOG = WLOG_;
     static constexpr int W = 1 << WLOG;               // lanes per codeword (list size rounded up to a power of two)
     static constexpr int G = 32 / W;                  // codewords per warp
-    static_assert(WLOG >= 2 && WLOG <= 5, "4..32 lanes per codeword");
+    static_assert(WLOG >= 0 && WLOG <= 5, "1..32 lanes per codeword");
     static constexpr int N = 1 << NLOG;
     static constexpr int MT = N >> T;                 // rows of the first per-path layer
     static constexpr int NW = N / 32;
