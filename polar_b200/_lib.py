@@ -3,7 +3,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_DIR = os.path.join(PKG, "lib")
+# POLAR_B200_LIB_DIR points the loader at another build of the same two libraries (A/B runs of kernel variants)
+LIB_DIR = os.environ.get("POLAR_B200_LIB_DIR") or os.path.join(PKG, "lib")
 DEV_SO = os.path.join(LIB_DIR, "libpolar_b200.so")
 HOST_SO = os.path.join(LIB_DIR, "libpolar_host.so")
 

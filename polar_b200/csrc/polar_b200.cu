@@ -753,6 +753,20 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST(11, 3, 5, 5, 4, 4),     // 11: N=2048 lists 17..32, layers 3-4 in the scratch
     POLAR_FAST(11, 3, 6, 5, 4, 5),     // 12: N=2048 lists 17..32, layers 3-5 in the scratch, 20 warps/SM
     POLAR_FAST(9, 3, 4, 5, 4, 5),      // 13: N=512 lists 17..32, layer 3 in the scratch
+    // one block per SM; the warps of a sub-partition start every codeword together (shared L0 instruction cache).
+    // Same placement as entries 0-5 / 6-11. Preferred by pick_fast_variant() unless POLAR_B200_SYNC=0.
+    POLAR_FAST_TM(11, 3, 5, 5, 16, 1), // 18: N=2048 lists 17..32
+    POLAR_FAST_TM(11, 3, 5, 4, 16, 1),
+    POLAR_FAST_TM(11, 3, 5, 3, 16, 1),
+    POLAR_FAST_TM(11, 3, 5, 2, 16, 1),
+    POLAR_FAST_TM(11, 3, 5, 1, 16, 1),
+    POLAR_FAST_TM(11, 3, 5, 0, 16, 1),
+    POLAR_FAST_TM(9, 3, 4, 5, 20, 1),  // 24: N=512 lists 17..32
+    POLAR_FAST_TM(9, 3, 4, 4, 20, 1),
+    POLAR_FAST_TM(9, 3, 4, 3, 20, 1),
+    POLAR_FAST_TM(9, 3, 4, 2, 20, 1),
+    POLAR_FAST_TM(9, 3, 4, 1, 20, 1),
+    POLAR_FAST_TM(9, 3, 4, 0, 20, 1),
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
@@ -764,6 +778,13 @@ int pick_fast_variant(int n, int L) {
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
     if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n && kFastVariants[forced].wlog == wlog)
         return forced;
+    // one-block-per-SM variants with the per-round barrier: measured +25% (N=2048) / +19% (N=512) at list 32, where a
+    // batch is many rounds per warp; -13..-19% for lists <= 4 at 65536 codewords (few rounds, heavier-tailed rounds).
+    // POLAR_B200_SYNC: 0 = never, 1 = one codeword per warp only (default), 2 = always.
+    const int sync = env_int("POLAR_B200_SYNC", 1);
+    if (sync >= 2 || (sync == 1 && wlog == 5))
+        for (int i = 0; i < kNumFastVariants; ++i)
+            if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog && kFastVariants[i].wpb > 4) return i;
     for (int i = 0; i < kNumFastVariants; ++i)
         if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog) return i;
     return -1;

@@ -202,6 +202,65 @@ __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
     return b + __int_as_float(__float_as_int(a) ^ (int)(bit << 31));
 }
 
+// ---- two nodes per instruction: Blackwell's packed fp32 pipe (FADD2 / FMUL2 / FFMA2 on a register pair).
+// Every packed operation is the IEEE round-to-nearest operation of its two halves, so f_rule2 / g_top2 return
+// exactly the bits of two f_rule / g_rule calls; what changes is the instruction count (14 instead of 18
+// issue slots per check node, 2.5 instead of 4 per variable node). POLAR_PACKED=0 compiles the scalar forms.
+#ifndef POLAR_PACKED
+#define POLAR_PACKED 1
+#endif
+__device__ __forceinline__ float sign_min(float a, float b) {
+    return __int_as_float(__float_as_int(fminf(fabsf(a), fabsf(b))) |
+                          ((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000));
+}
+__device__ __forceinline__ void f_rule2(float a0, float b0, float a1, float b1, float& y0, float& y1) {
+#if POLAR_PACKED
+    const float2 A = make_float2(a0, a1);
+    const float2 S = __fadd2_rn(A, make_float2(b0, b1));
+    const float2 D = __fadd2_rn(A, make_float2(-b0, -b1));
+    const float2 nl = make_float2(-kLog2e, -kLog2e), one = make_float2(1.0f, 1.0f);
+    const float2 ES = __fmul2_rn(make_float2(fabsf(S.x), fabsf(S.y)), nl);
+    const float2 ED = __fmul2_rn(make_float2(fabsf(D.x), fabsf(D.y)), nl);
+    const float2 P = __fadd2_rn(make_float2(ex2_approx(ES.x), ex2_approx(ES.y)), one);
+    const float2 Q = __fadd2_rn(make_float2(ex2_approx(ED.x), ex2_approx(ED.y)), one);
+    const float2 LQ = make_float2(-lg2_approx(Q.x), -lg2_approx(Q.y));
+    const float2 DIFF = __fadd2_rn(make_float2(lg2_approx(P.x), lg2_approx(P.y)), LQ);
+    const float2 SC = make_float2((fmaxf(fabsf(a0), fabsf(b0)) < 40.0f) ? kLn2 : 0.0f,
+                                  (fmaxf(fabsf(a1), fabsf(b1)) < 40.0f) ? kLn2 : 0.0f);
+    const float2 R = __ffma2_rn(DIFF, SC, make_float2(sign_min(a0, b0), sign_min(a1, b1)));
+    y0 = R.x; y1 = R.y;
+#else
+    y0 = f_rule(a0, b0); y1 = f_rule(a1, b1);
+#endif
+}
+// variable node with the partial-sum bit delivered in bit 31 of w (the other bits of w are ignored)
+__device__ __forceinline__ float g_top(float a, float b, uint32_t w) {
+    return b + __int_as_float(__float_as_int(a) ^ (int)(w & 0x80000000u));
+}
+__device__ __forceinline__ void g_top2(float a0, float b0, uint32_t w0, float a1, float b1, uint32_t w1, float& y0,
+                                       float& y1) {
+#if POLAR_PACKED
+    const float2 R = __fadd2_rn(make_float2(b0, b1),
+                                make_float2(__int_as_float(__float_as_int(a0) ^ (int)(w0 & 0x80000000u)),
+                                            __int_as_float(__float_as_int(a1) ^ (int)(w1 & 0x80000000u))));
+    y0 = R.x; y1 = R.y;
+#else
+    y0 = g_top(a0, b0, w0); y1 = g_top(a1, b1, w1);
+#endif
+}
+// four nodes of one layer: y[j] = f(a[j], b[j]) or g(a[j], b[j], bit pos + j of word)
+template <bool ISG>
+__device__ __forceinline__ void node4(const float (&a)[4], const float (&b)[4], uint32_t word, int pos, float (&y)[4]) {
+    if constexpr (ISG) {
+        const uint32_t w = word << (28 - pos);                 // bit pos + j -> bit 28 + j
+        g_top2(a[0], b[0], w << 3, a[1], b[1], w << 2, y[0], y[1]);
+        g_top2(a[2], b[2], w << 1, a[3], b[3], w, y[2], y[3]);
+    } else {
+        f_rule2(a[0], b[0], a[1], b[1], y[0], y[1]);
+        f_rule2(a[2], b[2], a[3], b[3], y[2], y[3]);
+    }
+}
+
 // ---- one per-path layer in memory: X_LAM = f / g (X_{LAM-1}), T < LAM <= NLOG-5 ----
 template <class C, int LAM, bool ISG>
 __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
@@ -235,11 +294,7 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { a[j] = src[(i0 + j) * 32]; b[j] = src[(i0 + j + M) * 32]; }
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if constexpr (ISG) y[j] = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
-                else y[j] = f_rule(a[j], b[j]);
-            }
+            node4<ISG>(a, b, word, i0 & 31, y);
             if constexpr (DST_TM) tm_st4(w.tm + i0, y);
             else {
 #pragma unroll
@@ -269,13 +324,10 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
                 const int nx = (i0 + 4 < M) ? i0 + 4 : i0;          // last group re-reads itself (harmless)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { na[j] = src[(nx + j) * 32]; nb[j] = src[(nx + j + M) * 32]; }
+                float y[4];
+                node4<ISG>(a, b, word, i0 & 31, y);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y;
-                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
-                    else y = f_rule(a[j], b[j]);
-                    dst[(i0 + j) * 32] = y;
-                }
+                for (int j = 0; j < 4; ++j) dst[(i0 + j) * 32] = y[j];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
             }
@@ -288,13 +340,10 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
                 float a[4], b[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { a[j] = src[(i0 + j) * 32]; b[j] = src[(i0 + j + M) * 32]; }
+                float y[4];
+                node4<ISG>(a, b, word, i0 & 31, y);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    float y;
-                    if constexpr (ISG) y = g_rule(a[j], b[j], (word >> ((i0 & 31) + j)) & 1u);
-                    else y = f_rule(a[j], b[j]);
-                    dst[(i0 + j) * 32] = y;
-                }
+                for (int j = 0; j < 4; ++j) dst[(i0 + j) * 32] = y[j];
             }
         }
     }
@@ -324,11 +373,10 @@ __device__ __forceinline__ void layer_to_regs(const Warp& w, const Lane& s, Sub&
             float a[4], b[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) { a[j] = src[(j0 + j) * 32]; b[j] = src[(j0 + j + 16) * 32]; }
+            float y[4];
+            node4<ISG>(a, b, field, j0, y);
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                if constexpr (ISG) r.x4[j0 + j] = g_rule(a[j], b[j], (field >> (j0 + j)) & 1u);
-                else r.x4[j0 + j] = f_rule(a[j], b[j]);
-            }
+            for (int j = 0; j < 4; ++j) r.x4[j0 + j] = y[j];
         }
     }
 }
@@ -339,18 +387,18 @@ __device__ __forceinline__ void sub_step(Sub& r, uint32_t sreg, bool isg, float&
     constexpr int M = 1 << K;
     const float* in = sub_arr<K + 1>(r);
     const uint32_t field = sreg >> (M - 1);
-    if (isg) {
+    if constexpr (K == 0) {
+        if (isg) lam_n = g_rule(in[0], in[1], field & 1u);
+        else lam_n = f_rule(in[0], in[1]);
+    } else if (isg) {
 #pragma unroll
-        for (int i = 0; i < M; ++i) {
-            const float y = g_rule(in[i], in[i + M], (field >> i) & 1u);
-            if constexpr (K == 0) lam_n = y; else sub_arr<K>(r)[i] = y;
-        }
+        for (int i = 0; i < M; i += 2)
+            g_top2(in[i], in[i + M], field << (31 - i), in[i + 1], in[i + 1 + M], field << (30 - i),
+                   sub_arr<K>(r)[i], sub_arr<K>(r)[i + 1]);
     } else {
 #pragma unroll
-        for (int i = 0; i < M; ++i) {
-            const float y = f_rule(in[i], in[i + M]);
-            if constexpr (K == 0) lam_n = y; else sub_arr<K>(r)[i] = y;
-        }
+        for (int i = 0; i < M; i += 2)
+            f_rule2(in[i], in[i + M], in[i + 1], in[i + 1 + M], sub_arr<K>(r)[i], sub_arr<K>(r)[i + 1]);
     }
 }
 
@@ -363,10 +411,36 @@ __device__ __forceinline__ void static_for(F&& f) {
     }
 }
 
+// inputs of layer-T node NODE for the betas q0 + 2H and q0 + 2H + 1 (q0 a multiple of 4): the bit-reversed channel
+// position of q0 + c is that of q0 plus a constant, so the four betas of a quad share one address computation
+template <class C, int NODE, int H>
+__device__ __forceinline__ void top_load_pair(const Warp& w, int q0, float (&v)[2][1 << (C::T - lead_zeros(NODE, C::T))]) {
+    constexpr int T = C::T, MT = C::MT, BITS = C::NLOG - T;
+    constexpr int S0 = lead_zeros(NODE, T);
+    constexpr int CNT = 1 << (T - S0);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        const int c = 2 * H + p;
+        if constexpr (S0 == 0) {
+            const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(q0, BITS)) +
+                               (CNT / 4) * (int)(cbrev(c, 2) << (BITS - 2));
+#pragma unroll
+            for (int q = 0; q < CNT / 4; ++q) {
+                const float4 t4 = POLAR_LDCHAN(c4 + q);
+                v[p][4 * q] = t4.x; v[p][4 * q + 1] = t4.y; v[p][4 * q + 2] = t4.z; v[p][4 * q + 3] = t4.w;
+            }
+        } else {
+            const float* xs = w.xs + C::xs_off(S0) + q0 + c;
+#pragma unroll
+            for (int i = 0; i < CNT; ++i) v[p][i] = xs[MT * (int)cbrev(i, T - S0)];
+        }
+    }
+}
+
 // ---- layer T node NODE (1 .. 2^T - 1) for every path, from the channel / shared arrays ----
 template <class C, int NODE>
 __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
-    constexpr int T = C::T, MT = C::MT, NLOG = C::NLOG;
+    constexpr int T = C::T, MT = C::MT, NLOG = C::NLOG, BITS = NLOG - T;
     constexpr int S0 = lead_zeros(NODE, T);          // values enter at level S0 (0 = channel)
     constexpr int CNT = 1 << (T - S0);
     constexpr bool DST_TM = C::TM && (C::LT == T);     // layer T itself lives in tensor memory
@@ -388,42 +462,34 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                     });
                 }
             });
-            auto load_inputs = [&](int beta, float (&v)[CNT]) {
-                if constexpr (S0 == 0) {
-                    const float4* c4 = reinterpret_cast<const float4*>(w.chan + (size_t)CNT * brev_bits(beta, NLOG - T));
-                    static_for<0, CNT / 4>([&](auto q_c) {
-                        constexpr int q = decltype(q_c)::value;
-                        const float4 t4 = POLAR_LDCHAN(c4 + q);
-                        v[4 * q] = t4.x; v[4 * q + 1] = t4.y; v[4 * q + 2] = t4.z; v[4 * q + 3] = t4.w;
-                    });
-                } else {
-                    const float* xs = w.xs + C::xs_off(S0);
-                    static_for<0, CNT>([&](auto i_c) {
-                        constexpr int i = decltype(i_c)::value;
-                        v[i] = xs[beta + MT * (int)cbrev(i, T - S0)];
-                    });
-                }
-            };
-            float nv[CNT];
-            load_inputs(wd * 32, nv);
-#pragma unroll 1
-            for (int bi = 0; bi < 32; ++bi) {
-                const int beta = wd * 32 + bi;
-                float v[CNT];
-#pragma unroll
-                for (int i = 0; i < CNT; ++i) v[i] = nv[i];
-                load_inputs(wd * 32 + ((bi + 1) & 31), nv);        // next beta of this word (wraps harmlessly)
+            // two betas at a time (wd * 32 + bi and + 1), so that every check node has a partner for the packed pipe
+            auto compute_pair = [&](int bi, float (&v)[2][CNT]) {
                 static_for<S0 + 1, T + 1>([&](auto lev_c) {
                     constexpr int lev = decltype(lev_c)::value;
                     constexpr bool isg = (NODE >> (T - lev)) & 1;
                     static_for<0, (1 << (T - lev))>([&](auto i_c) {
                         constexpr int i = decltype(i_c)::value;
-                        if constexpr (isg) v[i] = g_rule(v[2 * i], v[2 * i + 1], (sw[(1 << (T - lev)) + i] >> bi) & 1u);
-                        else v[i] = f_rule(v[2 * i], v[2 * i + 1]);
+                        if constexpr (isg) {
+                            const uint32_t word = sw[(1 << (T - lev)) + i];
+                            g_top2(v[0][2 * i], v[0][2 * i + 1], word << (31 - bi), v[1][2 * i], v[1][2 * i + 1],
+                                   word << (30 - bi), v[0][i], v[1][i]);
+                        } else {
+                            f_rule2(v[0][2 * i], v[0][2 * i + 1], v[1][2 * i], v[1][2 * i + 1], v[0][i], v[1][i]);
+                        }
                     });
                 });
-                if constexpr (DST_TM) tm_st1(w.tm + beta, v[0]);
-                else dst[beta * 32] = v[0];
+                const int beta = wd * 32 + bi;
+                if constexpr (DST_TM) { tm_st1(w.tm + beta, v[0][0]); tm_st1(w.tm + beta + 1, v[1][0]); }
+                else { dst[beta * 32] = v[0][0]; dst[(beta + 1) * 32] = v[1][0]; }
+            };
+            float va[2][CNT], vb[2][CNT];
+            top_load_pair<C, NODE, 0>(w, wd * 32, va);
+#pragma unroll 1
+            for (int bi = 0; bi < 32; bi += 4) {
+                top_load_pair<C, NODE, 1>(w, wd * 32 + bi, vb);
+                compute_pair(bi, va);
+                top_load_pair<C, NODE, 0>(w, wd * 32 + ((bi + 4) & 31), va);   // wraps harmlessly
+                compute_pair(bi + 2, vb);
             }
         }
         if constexpr (DST_TM) tm_wait_st();
@@ -787,18 +853,23 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     w.stack = w.srcof + 32;
     constexpr int W = C::W, G = C::G;
     w.tm = 0;
+    // NQ warps share one SM sub-partition (warp index mod 4), i.e. one L0 instruction cache and one TMEM lane quadrant
+    constexpr int NQ = WPB / 4;
+    static_assert(WPB % 4 == 0, "whole groups of four warps (one per TMEM lane quadrant)");
+    constexpr int TM_ALLOC = C::TM_COLS * NQ <= 32 ? 32 : C::TM_COLS * NQ <= 64 ? 64 : C::TM_COLS * NQ <= 128 ? 128
+                             : C::TM_COLS * NQ <= 256 ? 256 : 512;
     if constexpr (C::TM) {
-        static_assert(WPB == 4, "one warp per TMEM lane quadrant");
+        static_assert(C::TM_COLS * NQ <= 512, "tensor memory has 512 columns");
         __shared__ uint32_t tm_base;
         if (wib == 0) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
-                         :: "r"((uint32_t)__cvta_generic_to_shared(&tm_base)), "r"((uint32_t)C::TM_COLS) : "memory");
+                         :: "r"((uint32_t)__cvta_generic_to_shared(&tm_base)), "r"((uint32_t)TM_ALLOC) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        w.tm = tm_base + ((uint32_t)(wib * 32) << 16);
+        w.tm = tm_base + ((uint32_t)((wib & 3) * 32) << 16) + (uint32_t)((wib >> 2) * C::TM_COLS);
     }
     const int gbase = lane & ~(W - 1), slot = lane & (W - 1), grp_in_warp = lane / W;
     w.gx = a.gx + C::GX_FLOATS * gwarp;
@@ -807,7 +878,17 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     const int L = a.L, KW = (a.K + 31) >> 5;
     const int c0 = L - 1;                          // first path popped from the free stack (PolarCode.cpp:250-263)
 
-    for (int grp = gwarp; grp * G < a.B; grp += total_warps) {
+    // Every warp runs the same number of rounds. With more than one warp per sub-partition (NQ > 1) the warps that
+    // share a sub-partition start each round together (named barrier 1 + quadrant): they then walk through the same
+    // code at about the same time and share the sub-partition's small L0 instruction cache instead of evicting each
+    // other's loops -- unsynchronised warps drift apart over the rounds and instruction fetch becomes the largest
+    // single stall (profiles/r01_icache_*).
+    const int groups = (a.B + G - 1) / G;
+    const int rounds = (groups + total_warps - 1) / total_warps;
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+        const int grp = gwarp + rnd * total_warps;
+        if constexpr (NQ > 1) asm volatile("bar.sync %0, %1;" :: "r"(1 + (wib & 3)), "r"(NQ * 32) : "memory");
+        if (grp >= groups) continue;
         const int cw = grp * G + grp_in_warp;
         const bool valid = cw < a.B;
         w.chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
@@ -935,7 +1016,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         __syncthreads();
         if (wib == 0)
             asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;"
-                         :: "r"(w.tm & 0x0000FFFFu), "r"((uint32_t)C::TM_COLS) : "memory");
+                         :: "r"(w.tm & 0x0000FFFFu), "r"((uint32_t)TM_ALLOC) : "memory");
     }
 }
 
