@@ -610,7 +610,8 @@ struct polar_b200_ctx {
     int last_chunks = 0;
     float* d_fgx = nullptr;                // scratch of the fast kernel
     uint32_t* d_fgs = nullptr;
-    int fast_variant = -1, fast_warps = 0;
+    int fast_variant = -1;
+    size_t fgx_bytes = 0, fgs_bytes = 0;   // capacity of the two scratch buffers (shared by all variants, grown on demand)
     size_t l2_window = 0;
     float l2_ratio = 1.0f;
     long long launches = 0;
@@ -767,10 +768,16 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST_TM(9, 3, 4, 2, 20, 1),
     POLAR_FAST_TM(9, 3, 4, 1, 20, 1),
     POLAR_FAST_TM(9, 3, 4, 0, 20, 1),
+    POLAR_FAST_TM(10, 3, 5, 5, 16, 1), // 30: N=1024 lists 17..32
+    POLAR_FAST_TM(12, 3, 6, 5, 16, 1), // 31: N=4096 lists 17..32
+    POLAR_FAST(8, 3, 3, 5, 16, 1),     // 32: N=256 lists 17..32
+    // alternates (POLAR_B200_FAST_VARIANT=<index>)
+    POLAR_FAST(11, 3, 6, 5, 20, 1),    // 33: N=2048 lists 17..32 without tensor memory, 20 warps/SM
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
-int pick_fast_variant(int n, int L) {
+int pick_fast_variant(const polar_b200_ctx* c, int L, int B) {
+    const int n = c->n;
     if (env_int("POLAR_B200_FORCE_GENERIC", 0)) return -1;
     int wlog = 0;
     while ((1 << wlog) < L) ++wlog;                 // lanes per codeword
@@ -778,15 +785,22 @@ int pick_fast_variant(int n, int L) {
     const int forced = env_int("POLAR_B200_FAST_VARIANT", -1);
     if (forced >= 0 && forced < kNumFastVariants && kFastVariants[forced].nlog == n && kFastVariants[forced].wlog == wlog)
         return forced;
-    // one-block-per-SM variants with the per-round barrier: measured +25% (N=2048) / +19% (N=512) at list 32, where a
-    // batch is many rounds per warp; -13..-19% for lists <= 4 at 65536 codewords (few rounds, heavier-tailed rounds).
-    // POLAR_B200_SYNC: 0 = never, 1 = one codeword per warp only (default), 2 = always.
+    // One-block-per-SM variants with the per-round barrier. Measured on B200: +25% (N=2048) / +19% (N=512) at list 32
+    // for any batch of 8+ rounds per warp; for lists <= 4 +15% at 14 rounds per warp but -13..-19% at 3.5 rounds
+    // (nothing to re-synchronise yet, and the warps of a sub-partition wait for the slowest of them every round).
+    // POLAR_B200_SYNC: 0 = never; 1 (default) = always with one codeword per warp (lists 17..32), otherwise when the
+    // batch is at least kSyncMinRounds rounds per warp; 2 = always.
+    constexpr int kSyncMinRounds = 6;
     const int sync = env_int("POLAR_B200_SYNC", 1);
-    if (sync >= 2 || (sync == 1 && wlog == 5))
-        for (int i = 0; i < kNumFastVariants; ++i)
-            if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog && kFastVariants[i].wpb > 4) return i;
+    if (sync >= 1)
+        for (int i = 0; i < kNumFastVariants; ++i) {
+            const FastVariant& v = kFastVariants[i];
+            if (v.nlog != n || v.wlog != wlog || v.wpb <= 4) continue;
+            const long long per_round = (long long)c->sm_count * v.bps * v.wpb * (32 >> wlog);
+            if (sync >= 2 || wlog == 5 || (long long)B >= kSyncMinRounds * per_round) return i;
+        }
     for (int i = 0; i < kNumFastVariants; ++i)
-        if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog) return i;
+        if (kFastVariants[i].nlog == n && kFastVariants[i].wlog == wlog && kFastVariants[i].wpb <= 4) return i;
     return -1;
 }
 
@@ -822,14 +836,22 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     const FastVariant& v = kFastVariants[variant];
     int blocks = c->sm_count * v.bps;
     const int warps = blocks * v.wpb;
-    if (c->fast_variant != variant || c->fast_warps < warps) {
+    const size_t need_gx = v.gx_floats * warps * sizeof(float), need_gs = v.gs_words * warps * sizeof(uint32_t);
+    if (need_gx > c->fgx_bytes) {
         if (c->d_fgx) cudaFree(c->d_fgx);
+        c->d_fgx = nullptr; c->fgx_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_fgx, need_gx));
+        c->fgx_bytes = need_gx;
+    }
+    if (need_gs > c->fgs_bytes) {
         if (c->d_fgs) cudaFree(c->d_fgs);
-        c->d_fgx = nullptr; c->d_fgs = nullptr;
-        CU_TRY(cudaMalloc(&c->d_fgx, v.gx_floats * warps * sizeof(float)));
-        CU_TRY(cudaMalloc(&c->d_fgs, v.gs_words * warps * sizeof(uint32_t)));
+        c->d_fgs = nullptr; c->fgs_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_fgs, need_gs));
+        c->fgs_bytes = need_gs;
+    }
+    if (c->fast_variant != variant) {
         CU_TRY(v.prepare());
-        c->fast_variant = variant; c->fast_warps = warps;
+        c->fast_variant = variant;
         c->scratch_bytes = (v.gx_floats * sizeof(float) + v.gs_words * sizeof(uint32_t)) * warps;
         // optional: pin the per-warp LLR scratch in L2 with an access-policy window. Measured on
         // B200 (profiles/): no gain over the default LRU behaviour (-1..-4%), so it is off by default.
@@ -997,7 +1019,7 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int fv = pick_fast_variant(c->n, L);
+    const int fv = pick_fast_variant(c, L, B);
     if (fv >= 0) return decode_fast(c, fv, llr, B, L, info_packed, st);
     return decode_generic<float>(c, llr, B, L, info_packed, st);
 }
@@ -1021,22 +1043,23 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
     }
     // Chunks are whole "rounds" of the persistent grid (every warp decodes the same number of
     // codewords per chunk), so splitting costs no extra tail; about 6 chunks hide the PCIe time.
-    int per_round;
-    {
-        const int fv = pick_fast_variant(c->n, L);
-        if (fv >= 0) {
-            per_round = c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);
-        } else {
-            LaunchPlan p = make_plan(c, 4);
-            int W = 1; while (W < L) W <<= 1;
-            per_round = p.blocks * p.wpb * (32 / W);
-        }
-    }
-    // Chunks are whole rounds of the persistent grid (a chunk smaller than a round takes as long as
-    // a full one, the decode being latency-bound per warp), about 6 of them hide the PCIe time.
-    const int rounds = (B + per_round - 1) / per_round;
-    long long chunk = (long long)((rounds + 5) / 6) * per_round;
-    if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || chunk <= 0) chunk = B;
+    // The kernel variant is chosen for the chunk size (every launch is one chunk).
+    auto round_size = [&](int fv) {
+        if (fv >= 0) return c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);
+        LaunchPlan p = make_plan(c, 4);
+        int W = 1; while (W < L) W <<= 1;
+        return p.blocks * p.wpb * (32 / W);
+    };
+    auto chunk_size = [&](int per_round) {
+        const int rounds = (B + per_round - 1) / per_round;
+        long long ch = (long long)((rounds + 5) / 6) * per_round;
+        if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || ch <= 0 || ch > B) ch = B;
+        return ch;
+    };
+    int fv = pick_fast_variant(c, L, B);
+    long long chunk = chunk_size(round_size(fv));
+    const int fv2 = pick_fast_variant(c, L, (int)chunk);
+    if (fv2 != fv) { fv = fv2; chunk = chunk_size(round_size(fv)); }
     int nchunks = (int)((B + chunk - 1) / chunk);
     if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
     c->last_chunks = nchunks;
@@ -1049,7 +1072,7 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
                                cudaMemcpyHostToDevice, c->st_h2d));
         CU_TRY(cudaEventRecord(c->ev_in[i], c->st_h2d));
         CU_TRY(cudaStreamWaitEvent(c->st_run, c->ev_in[i], 0));
-        int rc = polar_b200_decode_scl_llr(c, d_in, nb, L, d_o, c->st_run);
+        int rc = fv >= 0 ? decode_fast(c, fv, d_in, nb, L, d_o, c->st_run) : decode_generic<float>(c, d_in, nb, L, d_o, c->st_run);
         if (rc) return rc;
         CU_TRY(cudaEventRecord(c->ev_done[i], c->st_run));
         CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_done[i], 0));
