@@ -43,7 +43,7 @@ enum {
     POLAR_B200_E_UNSUPPORTED = -2,/* valid for the reference, not for this build     */
     POLAR_B200_E_NOGPU = -3,      /* no usable CUDA device: there is NO CPU fallback */
     POLAR_B200_E_BATCH = -4,      /* B exceeds the ctx's max_batch                   */
-    POLAR_B200_E_LIST = -5        /* list size < 1, > max_list or > 32               */
+    POLAR_B200_E_LIST = -5        /* list size < 1, > max_list or > 127              */
 };
 
 /* ABI version of this header; polar_b200_abi_version() must return the same value. */
@@ -70,7 +70,8 @@ int polar_b200_info_words(int K);
  *   info_order   [K + crc_bits] = prefix of _channel_order_descending: position of info
  *                bit j (j < K) and of parity bit r (at K + r)
  *   crc_matrix   [crc_bits][K] row-major 0/1 (_crc_matrix); may be NULL when crc_bits == 0
- *   max_list     largest list size that will be requested (1..32)
+ *   max_list     largest list size that will be requested (1..127, the reference's own limit:
+ *                its loop counters are uint8_t, PolarCode.cpp:497-605)
  *   max_batch    largest B for the *_host entry points (sizes the staging buffers;
  *                the device-pointer entry points accept any B)
  */
@@ -85,7 +86,9 @@ int polar_b200_destroy(polar_b200_ctx* ctx);
  *   std::vector<uint8_t> PolarCode::decode_scl_llr(std::vector<double> llr, uint16_t list_size)
  * (PolarCode.h:32, PolarCode.cpp:130-190, 422-644).
  *   llr          device, [B][N] row-major fp32, the reference's channel order
- *   L            list size, 1 <= L <= max_list (L = 1 is plain SC); need not be a power of two
+ *   L            list size, 1 <= L <= max_list (L = 1 is plain SC); need not be a power of two.
+ *                Lists up to 32 run one codeword (or several) per warp; lists 33..127 run one
+ *                codeword per 64- or 128-thread block (same rules, lower throughput)
  *   info_packed  device, [B][polar_b200_info_words(K)]
  *   cuda_stream  a cudaStream_t (NULL = default stream); the call is asynchronous on it
  */
@@ -148,7 +151,8 @@ enum {
     POLAR_B200_INFO_BLOCKS = 3,          /* grid size of the last decode launch             */
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
-    POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode */
+    POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode,
+                                            -2 = wide-list kernel (lists 33..127), -3 = wide-list kernel in f64 */
     POLAR_B200_INFO_HOST_CHUNKS = 7      /* chunks the last *_host call was pipelined in            */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);

@@ -104,7 +104,7 @@ polar_b200_ctx* PolarCode::device_ctx(int min_batch) {
         std::copy(_crc_matrix[r].begin(), _crc_matrix[r].end(), flat.begin() + (size_t)r * _info_length);
     int batch = std::max(min_batch, 1);
     check(polar_b200_create(&_ctx, device, _n, _info_length, _crc_size, _frozen_bits.data(),
-                            _channel_order_descending.data(), _crc_size ? flat.data() : nullptr, 32, batch),
+                            _channel_order_descending.data(), _crc_size ? flat.data() : nullptr, 127, batch),
           "polar_b200_create");
     _ctx_batch = batch;
     return _ctx;

@@ -42,6 +42,7 @@
 
 namespace {
 
+constexpr int kMaxList = 127;       // the reference's own limit (uint8_t loop counters, PolarCode.cpp:497-605)
 constexpr int kMaxN = 13;          // log2 block length supported by the pointer packing (12 x 5 bits)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
@@ -149,6 +150,7 @@ __device__ __forceinline__ int get_ptr(unsigned long long p, int idx) { return (
 }  // namespace
 
 #include "scl_fast.cuh"
+#include "scl_wide.cuh"
 
 namespace {
 
@@ -608,6 +610,9 @@ struct polar_b200_ctx {
     static constexpr int kMaxChunks = 16;
     cudaEvent_t ev_in[kMaxChunks] = {}, ev_done[kMaxChunks] = {};
     int last_chunks = 0;
+    void* d_wgx = nullptr;                 // scratch of the wide-list kernel (lists 33..127), grow-only
+    uint32_t* d_wgs = nullptr;
+    size_t wgx_bytes = 0, wgs_bytes = 0;
     float* d_fgx = nullptr;                // scratch of the fast kernel
     uint32_t* d_fgs = nullptr;
     int fast_variant = -1;
@@ -778,7 +783,7 @@ constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]
 
 int pick_fast_variant(const polar_b200_ctx* c, int L, int B) {
     const int n = c->n;
-    if (env_int("POLAR_B200_FORCE_GENERIC", 0)) return -1;
+    if (env_int("POLAR_B200_FORCE_GENERIC", 0) || env_int("POLAR_B200_FORCE_WIDE", 0)) return -1;
     int wlog = 0;
     while ((1 << wlog) < L) ++wlog;                 // lanes per codeword
     if (L < 1 || wlog > 5) return -1;
@@ -830,6 +835,79 @@ int decode_generic(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* i
     c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes;
     c->last_kernel = sizeof(Real) == 8 ? -1 : 0;
     return POLAR_B200_OK;
+}
+
+// ---- lists 33..127: one block of W = 64 / 128 threads per codeword (scl_wide.cuh) ----
+template <class Real, int W>
+int decode_wide_w(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
+    const int n = c->n, elem = (int)sizeof(Real);
+    const int blocks_per_sm = env_int("POLAR_B200_WIDE_BPS", 1024 / W >= 8 ? 8 : 4);
+    const int budget = (200 * 1024) / blocks_per_sm;
+    const int fixed = W * (2 * elem + 32 + 12) + 16 * (W / 32);
+    auto s_rows_from = [&](int lam0) { int sr = 0; for (int lam = (lam0 < 1 ? 1 : lam0); lam <= n - 1; ++lam) sr += ((1 << (n - lam)) + 31) / 32; return sr; };
+    int lamS = n;
+    while (lamS > 1) {
+        const int cand = lamS - 1;
+        const int xr = (1 << (n - cand + 1)) - 2;
+        if (xr * W * elem + s_rows_from(cand) * W * 4 + fixed > budget) break;
+        lamS = cand;
+    }
+    wide::Args<Real> a;
+    memset(&a, 0, sizeof(a));
+    a.lamS = lamS;
+    a.smem_x_rows = (1 << (n - lamS + 1)) - 2;
+    const int lamSS = lamS < 1 ? 1 : lamS;
+    int off = 0;
+    for (int lam = 0; lam < lamSS; ++lam) { a.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
+    const size_t gs_rows = off;
+    off = 0;
+    for (int lam = lamSS; lam <= n - 1; ++lam) { a.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
+    a.smem_s_rows = off;
+    const size_t gx_rows = (size_t)(1 << n) - ((size_t)1 << (n - lamS + 1));
+    const int smem = a.smem_x_rows * W * elem + a.smem_s_rows * W * 4 + fixed;
+    int blocks = c->sm_count * blocks_per_sm;
+    if (blocks > B) blocks = B;
+    a.gx_stride = (gx_rows ? gx_rows : 1) * W;
+    a.gs_stride = (gs_rows ? gs_rows : 1) * W;
+    const size_t need_gx = a.gx_stride * (size_t)(c->sm_count * blocks_per_sm) * elem;
+    const size_t need_gs = a.gs_stride * (size_t)(c->sm_count * blocks_per_sm) * sizeof(uint32_t);
+    if (need_gx > c->wgx_bytes) {
+        if (c->d_wgx) cudaFree(c->d_wgx);
+        c->d_wgx = nullptr; c->wgx_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_wgx, need_gx));
+        c->wgx_bytes = need_gx;
+    }
+    if (need_gs > c->wgs_bytes) {
+        if (c->d_wgs) cudaFree(c->d_wgs);
+        c->d_wgs = nullptr; c->wgs_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_wgs, need_gs));
+        c->wgs_bytes = need_gs;
+    }
+    a.llr = llr; a.out = info_packed;
+    a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.gx = static_cast<Real*>(c->d_wgx); a.gs = c->d_wgs;
+    a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
+    CU_TRY(cudaFuncSetAttribute(wide::scl_wide_kernel<Real, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wide::scl_wide_kernel<Real, W><<<blocks, W, smem, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    c->last_wpb = W / 32; c->last_blocks = blocks; c->last_smem = smem;
+    c->last_kernel = sizeof(Real) == 8 ? -3 : -2;
+    c->scratch_bytes = c->wgx_bytes + c->wgs_bytes;
+    return POLAR_B200_OK;
+}
+
+template <class Real>
+int decode_wide(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
+    if (L <= 64) return decode_wide_w<Real, 64>(c, llr, B, L, info_packed, st);
+    return decode_wide_w<Real, 128>(c, llr, B, L, info_packed, st);
+}
+
+// any list size: lists <= 32 on one warp, 33..127 on one block per codeword
+template <class Real>
+int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
+    if (L > 32 || env_int("POLAR_B200_FORCE_WIDE", 0)) return decode_wide<Real>(c, llr, B, L, info_packed, st);
+    return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
 int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st) {
@@ -914,10 +992,10 @@ const char* polar_b200_strerror(int code) {
     switch (code) {
         case POLAR_B200_OK: return "ok";
         case POLAR_B200_E_ARG: return "polar_b200: invalid argument";
-        case POLAR_B200_E_UNSUPPORTED: return "polar_b200: parameter outside what this build supports (n <= 13, list <= 32)";
+        case POLAR_B200_E_UNSUPPORTED: return "polar_b200: parameter outside what this build supports (n <= 13, list <= 127)";
         case POLAR_B200_E_NOGPU: return "polar_b200: no usable CUDA device (there is no CPU fallback)";
         case POLAR_B200_E_BATCH: return "polar_b200: batch larger than the ctx's max_batch";
-        case POLAR_B200_E_LIST: return "polar_b200: list size must be in 1..min(max_list, 32)";
+        case POLAR_B200_E_LIST: return "polar_b200: list size must be in 1..min(max_list, 127)";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -938,7 +1016,7 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
     if (K + crc_bits > N) return POLAR_B200_E_ARG;
     if (crc_bits > 0 && !crc_matrix) return POLAR_B200_E_ARG;
     if (max_list < 1) return POLAR_B200_E_LIST;
-    if (max_list > 32) return POLAR_B200_E_UNSUPPORTED;
+    if (max_list > kMaxList) return POLAR_B200_E_UNSUPPORTED;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) { cudaGetLastError(); return POLAR_B200_E_NOGPU; }
     if (device < 0 || device >= ndev) return POLAR_B200_E_ARG;
@@ -1003,7 +1081,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
     cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
-    cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage);
+    cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs);
     if (c->st_h2d) {
         cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_run); cudaStreamDestroy(c->st_d2h);
         for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
@@ -1015,20 +1093,20 @@ int polar_b200_destroy(polar_b200_ctx* c) {
 int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
                               uint32_t* info_packed, void* cuda_stream) {
     if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
-    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int fv = pick_fast_variant(c, L, B);
     if (fv >= 0) return decode_fast(c, fv, llr, B, L, info_packed, st);
-    return decode_generic<float>(c, llr, B, L, info_packed, st);
+    return decode_any<float>(c, llr, B, L, info_packed, st);
 }
 
 int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int B, int L,
                                    uint32_t* info_packed_host, void* cuda_stream) {
     if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
     if (B > c->max_batch) return POLAR_B200_E_BATCH;
-    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     CU_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));     // work queued by the caller comes first
@@ -1056,6 +1134,16 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
         if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || ch <= 0 || ch > B) ch = B;
         return ch;
     };
+    if (L > 32 || env_int("POLAR_B200_FORCE_WIDE", 0)) {
+        // wide lists: one block per codeword, a single chunk on the run stream
+        CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, c->st_run));
+        int rc = decode_wide<float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
+        CU_TRY(cudaStreamSynchronize(c->st_run));
+        c->last_chunks = 1;
+        return POLAR_B200_OK;
+    }
     int fv = pick_fast_variant(c, L, B);
     long long chunk = chunk_size(round_size(fv));
     const int fv2 = pick_fast_variant(c, L, (int)chunk);
@@ -1086,23 +1174,23 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
 int polar_b200_decode_scl_llr_f64(polar_b200_ctx* c, const double* llr, int B, int L,
                                   uint32_t* info_packed, void* cuda_stream) {
     if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
-    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
-    return decode_generic<double>(c, llr, B, L, info_packed, (cudaStream_t)cuda_stream);
+    return decode_any<double>(c, llr, B, L, info_packed, (cudaStream_t)cuda_stream);
 }
 
 int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* c, const double* llr_host, int B, int L,
                                        uint32_t* info_packed_host, void* cuda_stream) {
     if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
     if (B > c->max_batch) return POLAR_B200_E_BATCH;
-    if (L < 1 || L > c->max_list || L > 32) return POLAR_B200_E_LIST;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (!c->d_llr64_stage) CU_TRY(cudaMalloc(&c->d_llr64_stage, (size_t)c->max_batch * c->N * sizeof(double)));
     CU_TRY(cudaMemcpyAsync(c->d_llr64_stage, llr_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = decode_generic<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
+    int rc = decode_any<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));

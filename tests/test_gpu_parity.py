@@ -87,6 +87,68 @@ def test_gpu_matches_oracle_on_awgn(torch_cuda, n, K, crc, L, B, eb):
     assert mism == 0, "%d of %d codewords differ from the oracle" % (mism, B)
 
 
+# lists 33..127 (PolarCode.cpp:497-605 uses uint8_t counters, so 127 is the reference's limit): one codeword per
+# 64- or 128-thread block
+WIDE = [
+    (9, 256, 16, 33, 48, 1.0),
+    (9, 256, 0, 64, 48, 1.0),
+    (9, 256, 16, 100, 32, 0.5),
+    (9, 256, 16, 127, 32, 0.5),
+    (11, 1024, 16, 48, 24, 1.0),
+    (11, 1024, 0, 127, 12, 1.0),
+    (7, 64, 8, 65, 50, 0.0),
+    (5, 16, 4, 127, 40, 0.0),      # 2^(K+crc) candidate paths > list only late: the list fills at the very end
+    (3, 4, 0, 40, 9, 0.0),         # fewer info bits than log2(L): the list never fills
+    (12, 2048, 16, 40, 4, 1.5),
+]
+
+
+@pytest.mark.parametrize("n,K,crc,L,B,eb", WIDE)
+def test_gpu_wide_lists_match_oracle(torch_cuda, n, K, crc, L, B, eb):
+    from polar_b200 import PolarCode
+    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+    info, llr = awgn_llrs(port, B, eb, seed=4000 + 37 * n + L)
+    want = port.decode_batch(llr, L, nthreads=os.cpu_count() or 1)
+    got = pc.decode_batch(llr, L)
+    assert pc.info(6) == -2
+    mism = int((got != want).any(1).sum())
+    assert mism == 0, "%d of %d codewords differ from the oracle" % (mism, B)
+    # device-pointer entry point, and the same decoder evaluated in double
+    import torch
+    out = pc.decode_device(torch.from_numpy(llr).cuda(), L)
+    from polar_b200 import unpack_bits
+    assert np.array_equal(unpack_bits(out.cpu().numpy().view(np.uint32), K), want)
+    if B * (1 << n) * L <= 48 * 512 * 127:
+        assert np.array_equal(pc.decode_batch_f64(llr.astype(np.float64), L), want)
+        assert pc.info(6) == -3
+
+
+def test_gpu_wide_kernel_on_short_lists_and_edge_cases(torch_cuda, monkeypatch):
+    """POLAR_B200_FORCE_WIDE=1 sends every list size through the block-per-codeword kernel: it must agree with
+    the oracle for short lists too, and on the edge rows (ties, zeros, overflowing metrics) at list 64."""
+    from polar_b200 import PolarCode
+    monkeypatch.setenv("POLAR_B200_FORCE_WIDE", "1")
+    for (n, K, crc, L, B, eb) in [(9, 256, 16, 1, 64, 2.0), (9, 256, 16, 8, 64, 1.0), (7, 64, 8, 3, 99, 0.5),
+                                  (11, 1024, 16, 32, 16, 1.25), (1, 1, 0, 1, 5, 0.0), (2, 2, 1, 4, 9, 0.0)]:
+        port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+        _, llr = awgn_llrs(port, B, eb, seed=600 + n + L)
+        got = pc.decode_batch(llr, L)
+        assert pc.info(6) == -2
+        assert np.array_equal(got, port.decode_batch(llr, L, nthreads=os.cpu_count() or 1))
+    monkeypatch.delenv("POLAR_B200_FORCE_WIDE")
+    for (n, K, crc) in [(9, 256, 16), (7, 64, 8)]:
+        e = load_edge(n, K, crc)
+        port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+        llr = e["llr"]
+        want = port.decode_batch(llr, 64, nthreads=os.cpu_count() or 1)
+        got = pc.decode_batch(llr, 64)
+        bad = [i for i in range(len(got)) if not np.array_equal(got[i], want[i])]
+        print("list 64 edge rows differing from the oracle (lattice rows allowed):", bad)
+        assert [i for i in bad if i not in LATTICE_ROWS] == []
+        got64 = pc.decode_batch_f64(llr.astype(np.float64), 64)
+        assert np.array_equal(got64, want)
+
+
 # rows of tests/golden/make_golden.py:edge_llrs whose LLRs sit on a lattice (+-40, integers, +-2): every
 # decision there is an exact cancellation (g = a - a) that the double-precision reference resolves by
 # the last-bit rounding noise of its literal exp/log formulas -- not reproducible in any other

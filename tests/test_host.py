@@ -43,7 +43,7 @@ def test_abi_argument_validation_needs_no_gpu(native_libs):
     assert lib.polar_b200_create(None, 0, 3, 4, 0, frozen, order, None, 1, 1) == -1
     assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 0, None, order, None, 1, 1) == -1
     assert lib.polar_b200_create(C.byref(ctx), 0, 14, 4, 0, frozen, order, None, 1, 1) == -2   # n too large
-    assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 0, frozen, order, None, 64, 1) == -2   # list too large
+    assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 0, frozen, order, None, 128, 1) == -2  # list too large (the reference's own limit is 127)
     assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 2, frozen, order, None, 1, 1) == -1    # crc without matrix
     assert lib.polar_b200_decode_scl_llr(None, None, 1, 1, None, None) == -1
     assert lib.polar_b200_destroy(None) == -1
