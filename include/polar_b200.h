@@ -119,6 +119,24 @@ int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* ctx, const double* llr_ho
                                        uint32_t* info_packed_host, void* cuda_stream);
 
 /*
+ * Probability-domain list decoder. Replaces B calls of
+ *   std::vector<uint8_t> PolarCode::decode_scl_p1(std::vector<double> p1, std::vector<double> p0, uint16_t list_size)
+ * (PolarCode.h:31, PolarCode.cpp:110-128 -> decode_scl :150-190 with recursivelyCalcP :375-420): tree entries are
+ * likelihood pairs, every refreshed layer is divided by its maximum over all live paths, forks are ranked by the
+ * likelihood pair (:510-514), the final pick takes the largest likelihood of the last decided bit (:631-637).
+ * Evaluated in double with individually rounded products (no FMA contraction), i.e. the reference's own
+ * arithmetic. Note the reference's argument order: p1 first.
+ *   p1, p0: [B][N] double, P(y_i | 1) and P(y_i | 0) in the reference's channel order; device pointers (first
+ *   form, asynchronous on the stream) or host pointers (second form, synchronous, B <= max_batch).
+ * The reference's BLER harness never calls this decoder (PolarCode.cpp:755 is commented out); it is provided so
+ * that the class surface is complete, on the block-per-codeword kernel (not the throughput path).
+ */
+int polar_b200_decode_scl_p1(polar_b200_ctx* ctx, const double* p1, const double* p0, int B, int L,
+                             uint32_t* info_packed, void* cuda_stream);
+int polar_b200_decode_scl_p1_host(polar_b200_ctx* ctx, const double* p1_host, const double* p0_host, int B, int L,
+                                  uint32_t* info_packed_host, void* cuda_stream);
+
+/*
  * Block-error flags: block_err[b] = 1 iff any of the K info bits differ. Replaces the
  * comparison loop of the BLER harness (PolarCode.cpp:758-764). All device pointers;
  * n_err (device, may be NULL) is incremented by the number of block errors.
@@ -152,7 +170,8 @@ enum {
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
     POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode,
-                                            -2 = wide-list kernel (lists 33..127), -3 = wide-list kernel in f64 */
+                                            -2 = wide-list kernel (lists 33..127), -3 = wide-list kernel in f64,
+                                            -4 = probability-domain decoder */
     POLAR_B200_INFO_HOST_CHUNKS = 7      /* chunks the last *_host call was pipelined in            */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);

@@ -331,6 +331,177 @@ struct Decoder {
     }
 };
 
+// ---- probability-domain decoder: PolarCode::decode_scl_p1 (PolarCode.cpp:110-128) -> decode_scl (:150-190)
+// with recursivelyCalcP (:375-420) in place of the LLR recursion. Double only, like the reference. Layer
+// arrays hold pairs (P(..|0), P(..|1)); after every layer refresh all values of all live paths are divided by
+// their common maximum (:392-418), which keeps path likelihoods comparable across the list; there is no
+// separate path metric: forks are ranked by the pair at the decision layer (:510-514) and the final pick takes
+// the largest likelihood of the last decided bit (:631-637).
+struct ProbDecoder {
+    const Code& c;
+    int L;
+    std::vector<size_t> off;
+    size_t tree = 0;
+    std::vector<double> pr;      // per path: 2 doubles per tree entry
+    std::vector<uint8_t> ps, bits, alive;
+    PathPool pool;
+
+    ProbDecoder(const Code& code, int list) : c(code), L(list) {
+        off.resize(c.n + 1);
+        for (int lam = 0; lam <= c.n; ++lam) { off[lam] = tree; tree += (size_t)1 << (c.n - lam); }
+        pr.resize(2 * tree * L);
+        ps.resize(2 * tree * L);
+        bits.resize((size_t)c.N * L);
+        alive.resize(L);
+    }
+    double* P(int l, int lam) { return &pr[2 * ((size_t)l * tree + off[lam])]; }
+    uint8_t* C(int l, int lam) { return &ps[2 * ((size_t)l * tree + off[lam])]; }
+    uint8_t* U(int l) { return &bits[(size_t)l * c.N]; }
+
+    // PolarCode.cpp:375-420
+    void calc_p(int lam, int phi) {
+        if (lam == 0) return;
+        if ((phi & 1) == 0) calc_p(lam - 1, phi >> 1);
+        const int M = 1 << (c.n - lam);
+        double sigma = 0.0;
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            double* y = P(l, lam);
+            const double* x = P(l, lam - 1);
+            const uint8_t* cs = C(l, lam);
+            for (int b = 0; b < M; ++b) {
+                if ((phi & 1) == 0) {                                                   // :392-396
+                    y[2 * b] = 0.5f * (x[2 * (2 * b)] * x[2 * (2 * b + 1)] + x[2 * (2 * b) + 1] * x[2 * (2 * b + 1) + 1]);
+                    y[2 * b + 1] = 0.5f * (x[2 * (2 * b) + 1] * x[2 * (2 * b + 1)] + x[2 * (2 * b)] * x[2 * (2 * b + 1) + 1]);
+                } else {                                                                // :398-402
+                    const uint8_t u = cs[2 * b];
+                    y[2 * b] = 0.5f * x[2 * (2 * b) + (u % 2)] * x[2 * (2 * b + 1)];
+                    y[2 * b + 1] = 0.5f * x[2 * (2 * b) + ((u + 1) % 2)] * x[2 * (2 * b + 1) + 1];
+                }
+                sigma = std::max(sigma, y[2 * b]);
+                sigma = std::max(sigma, y[2 * b + 1]);
+            }
+        }
+        if (sigma == 0) return;                                                          // :410-411 (underflow)
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            double* y = P(l, lam);
+            for (int b = 0; b < M; ++b) { y[2 * b] = y[2 * b] / sigma; y[2 * b + 1] = y[2 * b + 1] / sigma; }
+        }
+    }
+    // PolarCode.cpp:457-473 (same as the LLR decoder)
+    void update_c(int lam, int phi) {
+        const int psi = phi >> 1;
+        const int M = 1 << (c.n - lam);
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            const uint8_t* cs = C(l, lam);
+            uint8_t* up = C(l, lam - 1);
+            for (int b = 0; b < M; ++b) {
+                up[2 * (2 * b) + (psi & 1)] = cs[2 * b] ^ cs[2 * b + 1];
+                up[2 * (2 * b + 1) + (psi & 1)] = cs[2 * b + 1];
+            }
+        }
+        if (psi & 1) update_c(lam - 1, psi);
+    }
+    int clone(int l) {                                                                   // :274-288
+        const int lp = pool.take();
+        alive[lp] = 1;
+        std::copy(P(l, 0), P(l, 0) + 2 * tree, P(lp, 0));
+        std::copy(C(l, 0), C(l, 0) + 2 * tree, C(lp, 0));
+        return lp;
+    }
+    void kill(int l) { alive[l] = 0; pool.give(l); }                                     // :290-303
+    void frozen_step(int phi) {                                                          // :475-487 (no metric here)
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            C(l, c.n)[phi & 1] = 0;
+            U(l)[phi] = 0;
+        }
+    }
+    void info_step(int phi) {                                                            // :489-607
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        std::vector<double> fork(2 * L, nan), sorted;
+        int n_alive = 0;
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            fork[2 * l] = P(l, c.n)[0];                                                  // :510-514
+            fork[2 * l + 1] = P(l, c.n)[1];
+            sorted.push_back(fork[2 * l]);
+            sorted.push_back(fork[2 * l + 1]);
+            ++n_alive;
+        }
+        const int rho = std::min(2 * n_alive, L);
+        std::sort(sorted.begin(), sorted.end(), std::greater<double>());
+        const double thr = sorted.at(rho - 1);
+        std::vector<uint8_t> keep(2 * L, 0);
+        int kept = 0;
+        for (int i = 0; i < 2 * L && kept < rho; ++i)
+            if (fork[i] > thr) { keep[i] = 1; ++kept; }
+        for (int i = 0; i < 2 * L && kept < rho; ++i)
+            if (fork[i] == thr) { keep[i] = 1; ++kept; }
+        for (int l = 0; l < L; ++l)
+            if (alive[l] && !keep[2 * l] && !keep[2 * l + 1]) kill(l);
+        for (int l = 0; l < L; ++l) {
+            if (!keep[2 * l] && !keep[2 * l + 1]) continue;
+            if (keep[2 * l] && keep[2 * l + 1]) {
+                C(l, c.n)[phi & 1] = 0;
+                const int lp = clone(l);
+                C(lp, c.n)[phi & 1] = 1;
+                std::copy(U(l), U(l) + phi, U(lp));
+                U(l)[phi] = 0;
+                U(lp)[phi] = 1;
+            } else if (keep[2 * l]) {
+                C(l, c.n)[phi & 1] = 0;
+                U(l)[phi] = 0;
+            } else {
+                C(l, c.n)[phi & 1] = 1;
+                U(l)[phi] = 1;
+            }
+        }
+    }
+    bool parity_ok(const uint8_t* u) const {                                             // :93-108
+        for (int r = 0; r < c.crc; ++r) {
+            unsigned acc = 0;
+            for (int j = 0; j < c.K; ++j) acc ^= (unsigned)(c.crcm[(size_t)r * c.K + j] & u[c.order[j]]);
+            if ((acc & 1) != u[c.order[c.K + r]]) return false;
+        }
+        return true;
+    }
+    int pick(bool use_parity) {                                                          // :609-644
+        int best = 0;
+        double p_best = 0;
+        bool any = false;
+        for (int l = 0; l < L; ++l) {
+            if (!alive[l]) continue;
+            if (use_parity && !parity_ok(U(l))) continue;
+            any = true;
+            const double p = P(l, c.n)[C(l, c.n)[1]];                                    // :631-637
+            if (p_best < p) { best = l; p_best = p; }
+        }
+        if (any) return best;
+        return pick(false);
+    }
+    void run(const double* p1, const double* p0, uint8_t* info_out) {                    // :110-128, :150-175
+        std::fill(pr.begin(), pr.end(), 0.0);
+        std::fill(ps.begin(), ps.end(), 0);
+        std::fill(bits.begin(), bits.end(), 0);
+        std::fill(alive.begin(), alive.end(), 0);
+        pool.reset(L);
+        const int l0 = pool.take();
+        alive[l0] = 1;
+        double* ch = P(l0, 0);
+        for (int b = 0; b < c.N; ++b) { ch[2 * b] = p0[b]; ch[2 * b + 1] = p1[b]; }      // :121-124
+        for (int phi = 0; phi < c.N; ++phi) {
+            calc_p(c.n, phi);
+            if (c.frozen[phi]) frozen_step(phi); else info_step(phi);
+            if (phi & 1) update_c(c.n, phi);
+        }
+        const int w = pick(c.crc != 0);
+        for (int j = 0; j < c.K; ++j) info_out[j] = U(w)[c.order[j]];
+    }
+};
+
 template <class R>
 void decode_many(const Code& c, const float* llr, int lo, int hi, int L, int minsum_only, uint8_t* out) {
     Decoder<R> d(c, L, minsum_only);
@@ -389,6 +560,33 @@ void oracle_decode_scl_llr(void* h, const double* llr, int L, uint8_t* info_out)
     const Code& c = *static_cast<Code*>(h);
     Decoder<double> d(c, L, 0);
     d.run(llr, info_out);
+}
+
+// PolarCode.h:31 -- decode_scl_p1(p1, p0, list_size): note the argument order (p1 first).
+void oracle_decode_scl_p1(void* h, const double* p1, const double* p0, int L, uint8_t* info_out) {
+    const Code& c = *static_cast<Code*>(h);
+    ProbDecoder d(c, L);
+    d.run(p1, p0, info_out);
+}
+
+// B codewords, [B][N] doubles each; returns wall seconds.
+double oracle_decode_p1_batch(void* h, const double* p1, const double* p0, int B, int L, uint8_t* info_out, int nthreads) {
+    const Code& c = *static_cast<Code*>(h);
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > B) nthreads = B > 0 ? B : 1;
+    auto work = [&](int t) {
+        const int lo = (int)((long long)B * t / nthreads), hi = (int)((long long)B * (t + 1) / nthreads);
+        ProbDecoder d(c, L);
+        for (int b = lo; b < hi; ++b) d.run(p1 + (size_t)b * c.N, p0 + (size_t)b * c.N, info_out + (size_t)b * c.K);
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    if (nthreads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; ++t) th.emplace_back(work, t);
+        for (auto& x : th) x.join();
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 // B codewords of float LLRs, widened to `double` (precision 0) or kept in float with the

@@ -41,6 +41,8 @@ def dev():
         lib.polar_b200_count_errors.argtypes = [vp, vp, vp, ip, vp, vp, vp]
         lib.polar_b200_decode_scl_llr_f64.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_b200_decode_scl_llr_f64_host.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_decode_scl_p1.argtypes = [vp, vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_decode_scl_p1_host.argtypes = [vp, vp, vp, ip, ip, vp, vp]
         lib.polar_b200_synthesize.argtypes = [vp, C.c_ulonglong, C.c_longlong, ip, vp, ip, vp, vp, vp]
         lib.polar_b200_get_info.restype = C.c_longlong
         lib.polar_b200_get_info.argtypes = [vp, ip]
@@ -65,6 +67,8 @@ def host():
         lib.polar_host_decode_batch_packed.argtypes = [vp, vp, ip, ip, vp]
         lib.polar_host_decode_device.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_host_decode_batch_packed_f64.argtypes = [vp, vp, ip, ip, vp]
+        lib.polar_host_decode_p1_batch_packed.argtypes = [vp, vp, vp, ip, ip, vp]
+        lib.polar_host_decode_scl_p1.argtypes = [vp, vp, vp, ip, vp]
         lib.polar_host_set_exact.argtypes = [vp, ip]
         lib.polar_host_ctx.restype = vp
         lib.polar_host_ctx.argtypes = [vp, ip]

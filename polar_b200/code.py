@@ -112,6 +112,25 @@ class PolarCode:
                                                                        int(list_size), out.ctypes.data))
         return out if packed else unpack_bits(out, self.K)
 
+    # ---- PolarCode.h:31: probability-domain decoder (p1 first, like the reference) ----
+    def decode_scl_p1(self, p1, p0, list_size):
+        p1 = np.ascontiguousarray(p1, np.float64)
+        p0 = np.ascontiguousarray(p0, np.float64)
+        out = np.zeros(self.K, np.uint8)
+        _lib.check_host(_lib.host().polar_host_decode_scl_p1(self._h, p1.ctypes.data, p0.ctypes.data, int(list_size),
+                                                             out.ctypes.data))
+        return out
+
+    def decode_p1_batch(self, p1, p0, list_size, packed=False):
+        """[B][N] float64 likelihoods P(y|1), P(y|0) in host memory -> [B][K] bits (include/polar_b200.h:
+        polar_b200_decode_scl_p1_host)."""
+        p1 = np.ascontiguousarray(p1, np.float64).reshape(-1, self.N)
+        p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, self.N)
+        out = np.zeros((p1.shape[0], self.KW), np.uint32)
+        _lib.check_host(_lib.host().polar_host_decode_p1_batch_packed(self._h, p1.ctypes.data, p0.ctypes.data, p1.shape[0],
+                                                                      int(list_size), out.ctypes.data))
+        return out if packed else unpack_bits(out, self.K)
+
     def set_exact(self, exact=True):
         """decode_scl_llr / get_bler_quick in reference precision (double) from now on"""
         _lib.host().polar_host_set_exact(self._h, 1 if exact else 0)

@@ -154,10 +154,21 @@ std::vector<uint8_t> PolarCode::decode_scl_llr(std::vector<double> llr, uint16_t
     return decode_scl_llr_batch(f.data(), 1, list_size);
 }
 
-std::vector<uint8_t> PolarCode::decode_scl_p1(std::vector<double>, std::vector<double>, uint16_t) {
-    throw std::logic_error(
-        "PolarCode::decode_scl_p1: the probability-domain decoder (PolarC/PolarCode.cpp:110-128) is outside the "
-        "accelerated path; use decode_scl_llr");
+void PolarCode::decode_scl_p1_batch_packed(const double* p1, const double* p0, int B, uint16_t list_size, uint32_t* info_packed) {
+    if (list_size >= 128) throw std::invalid_argument("PolarCode: list_size must be < 128");
+    check(polar_b200_decode_scl_p1_host(device_ctx(B), p1, p0, B, list_size, info_packed, nullptr),
+          "polar_b200_decode_scl_p1_host");
+}
+
+// PolarCode.cpp:110-128: one codeword by value in (p1 first, then p0), K bytes out.
+std::vector<uint8_t> PolarCode::decode_scl_p1(std::vector<double> p1, std::vector<double> p0, uint16_t list_size) {
+    p1.at(_block_length - 1);          // the reference reads with .at(): short input throws std::out_of_range (:122-123)
+    p0.at(_block_length - 1);
+    std::vector<uint32_t> packed(info_words());
+    decode_scl_p1_batch_packed(p1.data(), p0.data(), 1, list_size, packed.data());
+    std::vector<uint8_t> out(_info_length);
+    for (int j = 0; j < _info_length; ++j) out[j] = (packed[j >> 5] >> (j & 31)) & 1u;
+    return out;
 }
 
 // PolarCode.cpp:658-785. Three phases instead of one nested loop:
@@ -312,6 +323,21 @@ int polar_host_decode_device(void* h, const float* llr_dev, int B, int L, uint32
 int polar_host_decode_batch_packed_f64(void* h, const double* llr, int B, int L, uint32_t* info_packed) {
     PolarCode* p = static_cast<PolarCode*>(h);
     return guarded([&] { p->decode_scl_llr_batch_packed_f64(llr, B, (uint16_t)L, info_packed); });
+}
+
+int polar_host_decode_p1_batch_packed(void* h, const double* p1, const double* p0, int B, int L, uint32_t* info_packed) {
+    PolarCode* p = static_cast<PolarCode*>(h);
+    return guarded([&] { p->decode_scl_p1_batch_packed(p1, p0, B, (uint16_t)L, info_packed); });
+}
+
+// single-codeword reference-shaped call (PolarCode.h:31)
+int polar_host_decode_scl_p1(void* h, const double* p1, const double* p0, int L, uint8_t* info_out) {
+    PolarCode* p = static_cast<PolarCode*>(h);
+    return guarded([&] {
+        const int N = p->block_length();
+        std::vector<uint8_t> out = p->decode_scl_p1(std::vector<double>(p1, p1 + N), std::vector<double>(p0, p0 + N), (uint16_t)L);
+        std::copy(out.begin(), out.end(), info_out);
+    });
 }
 
 void polar_host_set_exact(void* h, int exact) { static_cast<PolarCode*>(h)->exact_arithmetic = exact != 0; }

@@ -29,8 +29,8 @@ public:
 
     // PolarCode.h:30 / PolarCode.cpp:60-91. Host code (negligible next to decoding).
     std::vector<uint8_t> encode(std::vector<uint8_t> info_bits);
-    // PolarCode.h:31. Probability-domain list decoding is outside the accelerated path
-    // (the reference's harness never calls it, PolarCode.cpp:755 is commented out): throws.
+    // PolarCode.h:31 / PolarCode.cpp:110-128, 375-420. Probability-domain list decoding, one codeword, on the
+    // GPU in double (the reference's harness never calls it, PolarCode.cpp:755 is commented out).
     std::vector<uint8_t> decode_scl_p1(std::vector<double> p1, std::vector<double> p0, uint16_t list_size);
     // PolarCode.h:32 / PolarCode.cpp:130-190. One codeword, GPU, latency-bound; kept for source
     // compatibility. LLRs are rounded to float before decoding.
@@ -47,6 +47,8 @@ public:
     void decode_scl_llr_batch_packed(const float* llr, int B, uint16_t list_size, uint32_t* info_packed);
     // Reference-precision mode (double LLRs, the reference's literal formulas in double on the GPU).
     void decode_scl_llr_batch_packed_f64(const double* llr, int B, uint16_t list_size, uint32_t* info_packed);
+    // Probability domain, batched: p1, p0 host [B][N] doubles; packed output.
+    void decode_scl_p1_batch_packed(const double* p1, const double* p0, int B, uint16_t list_size, uint32_t* info_packed);
     // Device pointers, asynchronous on `cuda_stream` (a cudaStream_t).
     void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream);
 

@@ -599,6 +599,7 @@ struct polar_b200_ctx {
     void* d_gx = nullptr;                  // generic-kernel LLR scratch (float or double rows)
     int scratch_elem = 4;
     double* d_llr64_stage = nullptr;       // host entry point of the f64 mode
+    double* d_prob_stage = nullptr;        // host entry point of the probability-domain decoder: p0 then p1
     uint32_t* d_gs = nullptr;
     size_t gx_stride = 0, gs_stride = 0;   // per warp, elements
     int scratch_warps = 0;
@@ -838,12 +839,15 @@ int decode_generic(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* i
 }
 
 // ---- lists 33..127: one block of W = 64 / 128 threads per codeword (scl_wide.cuh) ----
-template <class Real, int W>
-int decode_wide_w(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
-    const int n = c->n, elem = (int)sizeof(Real);
+template <class Dom, int W>
+int decode_wide_w(polar_b200_ctx* c, const typename Dom::Real* in0, const typename Dom::Real* in1, int B, int L,
+                  uint32_t* info_packed, cudaStream_t st) {
+    using Real = typename Dom::Real;
+    using Val = typename Dom::Val;
+    const int n = c->n, elem = (int)sizeof(Val);
     const int blocks_per_sm = env_int("POLAR_B200_WIDE_BPS", 1024 / W >= 8 ? 8 : 4);
     const int budget = (200 * 1024) / blocks_per_sm;
-    const int fixed = W * (2 * elem + 32 + 12) + 16 * (W / 32);
+    const int fixed = W * (2 * (int)sizeof(Real) + 32 + 12) + (16 + 2 * (int)sizeof(Real)) * (W / 32);
     auto s_rows_from = [&](int lam0) { int sr = 0; for (int lam = (lam0 < 1 ? 1 : lam0); lam <= n - 1; ++lam) sr += ((1 << (n - lam)) + 31) / 32; return sr; };
     int lamS = n;
     while (lamS > 1) {
@@ -852,7 +856,7 @@ int decode_wide_w(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* in
         if (xr * W * elem + s_rows_from(cand) * W * 4 + fixed > budget) break;
         lamS = cand;
     }
-    wide::Args<Real> a;
+    wide::Args<Dom> a;
     memset(&a, 0, sizeof(a));
     a.lamS = lamS;
     a.smem_x_rows = (1 << (n - lamS + 1)) - 2;
@@ -883,24 +887,31 @@ int decode_wide_w(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* in
         CU_TRY(cudaMalloc(&c->d_wgs, need_gs));
         c->wgs_bytes = need_gs;
     }
-    a.llr = llr; a.out = info_packed;
+    a.in0 = in0; a.in1 = in1; a.out = info_packed;
     a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
-    a.gx = static_cast<Real*>(c->d_wgx); a.gs = c->d_wgs;
+    a.gx = static_cast<Val*>(c->d_wgx); a.gs = c->d_wgs;
     a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
-    CU_TRY(cudaFuncSetAttribute(wide::scl_wide_kernel<Real, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    wide::scl_wide_kernel<Real, W><<<blocks, W, smem, st>>>(a);
+    CU_TRY(cudaFuncSetAttribute(wide::scl_wide_kernel<Dom, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    wide::scl_wide_kernel<Dom, W><<<blocks, W, smem, st>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     c->last_wpb = W / 32; c->last_blocks = blocks; c->last_smem = smem;
-    c->last_kernel = sizeof(Real) == 8 ? -3 : -2;
+    c->last_kernel = Dom::kNormalise ? -4 : (sizeof(Real) == 8 ? -3 : -2);
     c->scratch_bytes = c->wgx_bytes + c->wgs_bytes;
     return POLAR_B200_OK;
 }
 
 template <class Real>
 int decode_wide(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
-    if (L <= 64) return decode_wide_w<Real, 64>(c, llr, B, L, info_packed, st);
-    return decode_wide_w<Real, 128>(c, llr, B, L, info_packed, st);
+    if (L <= 64) return decode_wide_w<wide::LlrDom<Real>, 64>(c, llr, nullptr, B, L, info_packed, st);
+    return decode_wide_w<wide::LlrDom<Real>, 128>(c, llr, nullptr, B, L, info_packed, st);
+}
+
+// probability domain (decode_scl_p1): any list size on the block-per-codeword kernel, double like the reference
+int decode_prob(polar_b200_ctx* c, const double* p0, const double* p1, int B, int L, uint32_t* info_packed, cudaStream_t st) {
+    if (L <= 32) return decode_wide_w<wide::ProbDom, 32>(c, p0, p1, B, L, info_packed, st);
+    if (L <= 64) return decode_wide_w<wide::ProbDom, 64>(c, p0, p1, B, L, info_packed, st);
+    return decode_wide_w<wide::ProbDom, 128>(c, p0, p1, B, L, info_packed, st);
 }
 
 // any list size: lists <= 32 on one warp, 33..127 on one block per codeword
@@ -1081,7 +1092,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_frozen); cudaFree(c->d_order); cudaFree(c->d_crc_masks);
     cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
-    cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs);
+    cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
     if (c->st_h2d) {
         cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_run); cudaStreamDestroy(c->st_d2h);
         for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
@@ -1191,6 +1202,36 @@ int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* c, const double* llr_host
     if (!c->d_llr64_stage) CU_TRY(cudaMalloc(&c->d_llr64_stage, (size_t)c->max_batch * c->N * sizeof(double)));
     CU_TRY(cudaMemcpyAsync(c->d_llr64_stage, llr_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
     int rc = decode_any<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
+    if (rc) return rc;
+    CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return POLAR_B200_OK;
+}
+
+int polar_b200_decode_scl_p1(polar_b200_ctx* c, const double* p1, const double* p0, int B, int L,
+                             uint32_t* info_packed, void* cuda_stream) {
+    if (!c || !p1 || !p0 || !info_packed || B < 0) return POLAR_B200_E_ARG;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    return decode_prob(c, p0, p1, B, L, info_packed, (cudaStream_t)cuda_stream);
+}
+
+int polar_b200_decode_scl_p1_host(polar_b200_ctx* c, const double* p1_host, const double* p0_host, int B, int L,
+                                  uint32_t* info_packed_host, void* cuda_stream) {
+    if (!c || !p1_host || !p0_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
+    if (B > c->max_batch) return POLAR_B200_E_BATCH;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    const size_t per = (size_t)c->max_batch * c->N;
+    if (!c->d_prob_stage) CU_TRY(cudaMalloc(&c->d_prob_stage, 2 * per * sizeof(double)));
+    double* d_p0 = c->d_prob_stage;
+    double* d_p1 = c->d_prob_stage + per;
+    CU_TRY(cudaMemcpyAsync(d_p0, p0_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_p1, p1_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = decode_prob(c, d_p0, d_p1, B, L, c->d_out_stage, st);
     if (rc) return rc;
     CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));

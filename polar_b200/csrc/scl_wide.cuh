@@ -9,19 +9,83 @@
 // order, clones popping in ascending path order (:555-570, :274-303), first path = L-1 (:250-263), final pick
 // = strictly smaller metric / lowest index, parity filter with fall-through (:609-644).
 //
+// The kernel is written once over a "domain": LLR domain (decode_scl_llr, float or double) or the reference's
+// probability domain (decode_scl_p1, PolarCode.cpp:110-128, 375-420: pairs of likelihoods per tree entry, every
+// refreshed layer divided by the maximum over all live paths, forks ranked by the likelihood pair itself).
+//
 // Included by polar_b200.cu after Arith<>, rmin/rmax and kMaxN are defined.
 #pragma once
 
 namespace wide {
 
-template <class Real>
+// ---- LLR domain: PolarCode.cpp:422-455 (f / g), :483, :505-506 (metrics) ----
+template <class R>
+struct LlrDom {
+    using Real = R;
+    using Val = R;
+    static constexpr bool kNormalise = false;
+    static __device__ __forceinline__ void load(const R* llr, const R*, size_t base, int i, Val& x0, Val& x1) {
+        x0 = llr[base + 2 * i]; x1 = llr[base + 2 * i + 1];
+    }
+    static __device__ __forceinline__ Val f(Val a, Val b) { return Arith<R>::f(a, b); }
+    static __device__ __forceinline__ Val g(Val a, Val b, uint32_t bit) { return b + (bit ? -a : a); }
+    static __device__ __forceinline__ R vmax(Val) { return 0; }
+    static __device__ __forceinline__ Val scale(Val v, R) { return v; }
+    // fork metrics, smaller = better (m = -probForks)
+    static __device__ __forceinline__ void forks(R pm, Val leaf, R& m0, R& m1) {
+        m0 = pm + Arith<R>::softplus(-leaf);
+        m1 = pm + Arith<R>::softplus(leaf);
+    }
+    static __device__ __forceinline__ R frozen(R pm, Val leaf) { return pm + Arith<R>::softplus(-leaf); }
+    static __device__ __forceinline__ R pick_init() { return Arith<R>::inf(); }
+};
+
+// ---- probability domain (double, the reference's own type): PolarCode.cpp:375-420, :510-514, :631-637 ----
+// Products and sums are written with explicit round-to-nearest intrinsics so that nvcc cannot contract
+// a*b + c*d into an FMA: the reference (g++ -O2, x86-64) rounds every product, and the decisions of exact-tie
+// inputs depend on that last bit.
+struct P2 { double p0, p1; };
+struct ProbDom {
+    using Real = double;
+    using Val = P2;
+    static constexpr bool kNormalise = true;
+    static __device__ __forceinline__ void load(const double* p0, const double* p1, size_t base, int i, Val& x0, Val& x1) {
+        x0.p0 = p0[base + 2 * i]; x0.p1 = p1[base + 2 * i];             // p_0[2 beta] = p0[beta], p_0[2 beta + 1] = p1[beta] (:121-124)
+        x1.p0 = p0[base + 2 * i + 1]; x1.p1 = p1[base + 2 * i + 1];
+    }
+    static __device__ __forceinline__ Val f(Val a, Val b) {               // :392-396
+        Val y;
+        y.p0 = __dmul_rn(0.5, __dadd_rn(__dmul_rn(a.p0, b.p0), __dmul_rn(a.p1, b.p1)));
+        y.p1 = __dmul_rn(0.5, __dadd_rn(__dmul_rn(a.p1, b.p0), __dmul_rn(a.p0, b.p1)));
+        return y;
+    }
+    static __device__ __forceinline__ Val g(Val a, Val b, uint32_t bit) { // :398-402
+        Val y;
+        y.p0 = __dmul_rn(__dmul_rn(0.5, bit ? a.p1 : a.p0), b.p0);
+        y.p1 = __dmul_rn(__dmul_rn(0.5, bit ? a.p0 : a.p1), b.p1);
+        return y;
+    }
+    static __device__ __forceinline__ double vmax(Val v) { return fmax(v.p0, v.p1); }
+    static __device__ __forceinline__ Val scale(Val v, double sigma) {    // :415-416
+        Val y; y.p0 = __ddiv_rn(v.p0, sigma); y.p1 = __ddiv_rn(v.p1, sigma); return y;
+    }
+    // "metric" = minus the likelihood, so that smaller = better as in the LLR domain; negation is exact
+    static __device__ __forceinline__ void forks(double, Val leaf, double& m0, double& m1) { m0 = -leaf.p0; m1 = -leaf.p1; }
+    static __device__ __forceinline__ double frozen(double, Val leaf) { return -leaf.p0; }
+    static __device__ __forceinline__ double pick_init() { return 0.0; }  // p_p1 = 0, strictly larger wins (:612, :634)
+};
+
+template <class Dom>
 struct Args {
-    const Real* llr;             // [B][N]
+    using Real = typename Dom::Real;
+    using Val = typename Dom::Val;
+    const Real* in0;             // [B][N] LLRs, or p0 in the probability domain
+    const Real* in1;             // unused, or p1
     uint32_t* out;               // [B][KW]
     const uint32_t* frozen_words;
     const uint16_t* info_order;  // [K + crc]
     const uint32_t* crc_masks;   // [crc][NW] over phi
-    Real* gx;                    // per-block LLR scratch rows (W values each)
+    Val* gx;                     // per-block LLR scratch rows (W values each)
     uint32_t* gs;                // per-block partial-sum scratch rows (W words each)
     unsigned long long gx_stride;// values per block
     unsigned long long gs_stride;// words per block
@@ -44,8 +108,10 @@ __device__ __forceinline__ void pset(Ptrs& p, int idx, unsigned col) {
     else p.hi = (p.hi & ~(255ull << sh)) | ((unsigned long long)col << sh);
 }
 
-template <class Real, int W>
-__global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
+template <class Dom, int W>
+__global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Dom> a) {
+    using Real = typename Dom::Real;
+    using Val = typename Dom::Val;
     constexpr int NWARP = W / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -53,8 +119,9 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
     const int NW = (N + 31) >> 5, KW = (a.K + 31) >> 5;
 
     // ---- shared memory carve-up ----
-    Real* sx = reinterpret_cast<Real*>(smem_raw);
-    unsigned char* p = smem_raw + (size_t)a.smem_x_rows * W * sizeof(Real);
+    Val* sx = reinterpret_cast<Val*>(smem_raw);
+    unsigned char* p = smem_raw + (size_t)a.smem_x_rows * W * sizeof(Val);
+    Real* red = reinterpret_cast<Real*>(p); p += 2 * NWARP * sizeof(Real);   // block-max scratch, double-buffered
     Real* x_m0 = reinterpret_cast<Real*>(p); p += W * sizeof(Real);
     Real* x_m1 = reinterpret_cast<Real*>(p); p += W * sizeof(Real);
     unsigned long long* x_plo = reinterpret_cast<unsigned long long*>(p); p += W * 8;   // staged px.lo, px.hi, ps.lo, ps.hi
@@ -70,10 +137,22 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
     uint32_t* b_clone = reinterpret_cast<uint32_t*>(p); p += NWARP * 4;
     uint32_t* b_misc = reinterpret_cast<uint32_t*>(p); p += NWARP * 4;
 
-    Real* gx = a.gx + a.gx_stride * blockIdx.x;
+    Val* gx = a.gx + a.gx_stride * blockIdx.x;
+    int red_parity = 0;
+    // maximum over the block; one barrier per call (the scratch alternates between two buffers)
+    auto block_max = [&](Real v) -> Real {
+        for (int o = 16; o > 0; o >>= 1) v = rmax<Real>(v, __shfl_xor_sync(FULL_MASK, v, o));
+        Real* buf = red + red_parity * NWARP;
+        if (lane == 0) buf[warp] = v;
+        __syncthreads();
+        Real r = buf[0];
+        for (int w = 1; w < NWARP; ++w) r = rmax<Real>(r, buf[w]);
+        red_parity ^= 1;
+        return r;
+    };
     uint32_t* gs = a.gs + a.gs_stride * blockIdx.x;
 
-    auto xrow = [&](int lam, int beta) -> Real* {
+    auto xrow = [&](int lam, int beta) -> Val* {
         if (lam >= lamS) return sx + (size_t)((1 << (n - lamS + 1)) - (1 << (n - lam + 1)) + beta) * W;
         return gx + (size_t)(N - (1 << (n - lam + 1)) + beta) * W;
     };
@@ -95,13 +174,13 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
     };
 
     for (int cw = blockIdx.x; cw < a.B; cw += gridDim.x) {
-        const Real* chan = a.llr + (size_t)cw * N;
+        const size_t chan = (size_t)cw * N;
         bool active = (tid == L - 1);           // PolarCode.cpp:259-263
         Real pm = 0;
         Ptrs px = {0ull, 0ull}, ps = {0ull, 0ull};
         uint32_t s_n = 0;
         int sp = L - 1;                         // stack height (uniform)
-        Real lam_n = 0;
+        Val lam_n = Val();
         uint32_t frozen_word = 0;
         stk[tid] = tid;
         __syncthreads();
@@ -112,32 +191,43 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
             for (int lam = lam_top; lam <= n; ++lam) {
                 const int M = 1 << (n - lam);
                 const bool is_g = (lam == lam_top) && (phi != 0);
-                const Real* src = nullptr;
+                const Val* src = nullptr;
                 if (lam > 1) src = xrow(lam - 1, 0) + pget(px, lam - 2);
                 const uint32_t* sw = nullptr;
                 if (is_g && lam < n) sw = srow(lam, 0) + pget(ps, lam - 1);
-                Real* dst = (lam < n) ? xrow(lam, 0) + tid : nullptr;
+                Val* dst = (lam < n) ? xrow(lam, 0) + tid : nullptr;
+                Real vm = 0;
                 if (active) {
                     for (int i = 0; i < M; ++i) {
-                        Real x0, x1;
+                        Val x0, x1;
                         int beta = i;
                         if (lam == 1) {
-                            x0 = chan[2 * i]; x1 = chan[2 * i + 1];
+                            // channel layer: reference pairs are (2k, 2k+1); the result lands at the bit-reversed position
+                            Dom::load(a.in0, a.in1, chan, i, x0, x1);
                             beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
                         } else {
                             x0 = src[(size_t)i * W];
                             x1 = src[(size_t)(i + M) * W];
                         }
-                        Real y;
+                        Val y;
                         if (is_g) {
                             uint32_t bit;
                             if (lam == n) bit = s_n & 1u;
                             else bit = (sw[(size_t)(beta >> 5) * W] >> (beta & 31)) & 1u;
-                            y = x1 + (bit ? -x0 : x0);                      // PolarCode.cpp:448-451
+                            y = Dom::g(x0, x1, bit);                        // PolarCode.cpp:448-451 / :398-402
                         } else {
-                            y = Arith<Real>::f(x0, x1);                     // PolarCode.cpp:438-446
+                            y = Dom::f(x0, x1);                             // PolarCode.cpp:438-446 / :392-396
                         }
+                        if (Dom::kNormalise) vm = rmax<Real>(vm, Dom::vmax(y));
                         if (lam == n) lam_n = y; else dst[(size_t)beta * W] = y;
+                    }
+                }
+                if (Dom::kNormalise) {
+                    // PolarCode.cpp:404-418: divide the refreshed layer of every live path by the common maximum
+                    const Real sigma = block_max(vm);
+                    if (sigma != 0 && active) {
+                        if (lam == n) lam_n = Dom::scale(lam_n, sigma);
+                        else for (int i = 0; i < M; ++i) dst[(size_t)i * W] = Dom::scale(dst[(size_t)i * W], sigma);
                     }
                 }
                 if (lam < n) pset(px, lam - 1, tid);
@@ -148,11 +238,11 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
             const bool frozen = (frozen_word >> (phi & 31)) & 1u;
             uint32_t u = 0;
             if (frozen) {
-                if (active) pm += Arith<Real>::softplus(-lam_n);            // PolarCode.cpp:475-487
+                if (active) pm = Dom::frozen(pm, lam_n);                    // PolarCode.cpp:475-487
             } else {
                 // PolarCode.cpp:489-607; metrics kept positive (m = -probForks)
-                const Real m0 = pm + Arith<Real>::softplus(-lam_n);
-                const Real m1 = pm + Arith<Real>::softplus(lam_n);
+                Real m0, m1;
+                Dom::forks(pm, lam_n, m0, m1);
                 x_m0[tid] = m0; x_m1[tid] = m1;
                 x_plo[tid] = px.lo; x_phi[tid] = px.hi; x_slo[tid] = ps.lo; x_shi[tid] = ps.hi; x_sn[tid] = s_n;
                 srcof[tid] = tid;
@@ -274,7 +364,7 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Real> a) {
         const bool use_parity = (a.crc != 0) && (total(b_misc) != 0);
         int win = 0;
         {
-            Real best = Arith<Real>::inf();
+            Real best = Dom::pick_init();
             bool found = false;
             for (int w = 0; w < NWARP; ++w) {
                 uint32_t bits = use_parity ? b_misc[w] : b_act[w];

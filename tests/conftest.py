@@ -47,6 +47,17 @@ def load_edge(n, K, crc):
     return out
 
 
+def p1_fixture_paths():
+    return sorted(glob.glob(os.path.join(GOLDEN, "p1_*.npz")))
+
+
+def load_p1(path):
+    z = np.load(path)
+    K = int(z["K"])
+    return dict(n=int(z["n"]), K=K, crc=int(z["crc"]), L=int(z["L"]), n_edge=int(z["n_edge"]), p1=z["p1"], p0=z["p0"],
+                decoded=np.unpackbits(z["decoded"], axis=-1)[:, :K])
+
+
 CONSTRUCTIONS = [(9, 256, 0), (9, 256, 16), (11, 1024, 0), (11, 1024, 16), (5, 16, 4), (7, 64, 8), (10, 512, 8)]
 
 

@@ -90,6 +90,14 @@ class _Base:
         self._f("decode_scl_llr")(self.h, llr, int(L), out)
         return out
 
+    def decode_p1_one(self, p1, p0, L):
+        """PolarCode.h:31 decode_scl_p1(p1, p0, list_size): probability-domain decoder, one codeword."""
+        fn = self._f("decode_scl_p1")
+        fn.argtypes = [C.c_void_p, _f64p, _f64p, C.c_int, _u8p]
+        out = np.zeros(self.K, np.uint8)
+        fn(self.h, np.ascontiguousarray(p1, np.float64), np.ascontiguousarray(p0, np.float64), int(L), out)
+        return out
+
 
 class Port(_Base):
     prefix = "oracle_"
@@ -113,6 +121,16 @@ class Port(_Base):
         out = np.zeros((llr.shape[0], self.K), np.uint8)
         self.last_seconds = self.lib.oracle_decode_batch(self.h, llr, llr.shape[0], int(L), out, int(nthreads),
                                                          int(precision), int(minsum_only))
+        return out
+
+    def decode_p1_batch(self, p1, p0, L, nthreads=1):
+        p1 = np.ascontiguousarray(p1, np.float64).reshape(-1, self.N)
+        p0 = np.ascontiguousarray(p0, np.float64).reshape(-1, self.N)
+        out = np.zeros((p1.shape[0], self.K), np.uint8)
+        fn = self.lib.oracle_decode_p1_batch
+        fn.restype = C.c_double
+        fn.argtypes = [C.c_void_p, _f64p, _f64p, C.c_int, C.c_int, _u8p, C.c_int]
+        self.last_seconds = fn(self.h, p1, p0, p1.shape[0], int(L), out, int(nthreads))
         return out
 
     def get_bler_quick(self, ebno, lists, max_err=100, max_runs=1000):
@@ -149,3 +167,40 @@ def awgn_llrs(code, B, ebno_db, seed):
     r = a * (2.0 * coded.astype(np.float64) - 1.0) + np.sqrt(0.5) * rng.standard_normal((B, code.N))
     llr = (-4.0 * r * a).astype(np.float32)
     return info, llr
+
+
+def awgn_probs(code, B, ebno_db, seed):
+    """Channel likelihoods for the probability-domain decoder, as in the reference's commented-out harness
+    lines PolarCode.cpp:749-751: p0 = exp(-(r + a)^2 / N0) / sqrt(pi N0), p1 = exp(-(r - a)^2 / N0) / sqrt(pi N0),
+    N0 = 1 (BPSK 0 -> -a, 1 -> +a). Returns (info [B][K] u8, p1 [B][N] f64, p0 [B][N] f64)."""
+    rng = np.random.Generator(np.random.Philox(key=seed))
+    info = rng.integers(0, 2, size=(B, code.K), dtype=np.uint8)
+    coded = code.encode(info)
+    a = 10.0 ** (ebno_db / 20.0) * np.sqrt(code.K / code.N)
+    r = a * (2.0 * coded.astype(np.float64) - 1.0) + np.sqrt(0.5) * rng.standard_normal((B, code.N))
+    p0 = np.exp(-(r + a) ** 2) / np.sqrt(np.pi)
+    p1 = np.exp(-(r - a) ** 2) / np.sqrt(np.pi)
+    return info, np.ascontiguousarray(p1), np.ascontiguousarray(p0)
+
+
+def edge_probs(N, seed=3):
+    """Edge inputs of the probability-domain decoder: exact ties (p0 == p1 everywhere), certain and impossible
+    symbols (exact 0 / 1), everything zero (the sigma == 0 underflow branch, PolarCode.cpp:410-411), denormal
+    magnitudes, and ties mixed with noise. Returns (p1 [R][N], p0 [R][N])."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    rows.append((np.full(N, 0.5), np.full(N, 0.5)))
+    rows.append((np.zeros(N), np.zeros(N)))
+    bits = rng.integers(0, 2, N).astype(np.float64)
+    rows.append((bits, 1.0 - bits))
+    rows.append((np.full(N, 0.3), np.full(N, 0.7)))
+    rows.append((np.full(N, 1e-300), np.full(N, 3e-300)))
+    p = rng.random(N)
+    mix = np.where(rng.random(N) < 0.5, 0.5, p)
+    rows.append((mix, 1.0 - mix))
+    p = rng.random(N)
+    rows.append((np.where(rng.random(N) < 0.3, 0.0, p), np.where(rng.random(N) < 0.3, 0.0, 1.0 - p)))
+    rows.append((np.full(N, 0.25), np.full(N, 0.25)))
+    p1 = np.stack([r[0] for r in rows]).astype(np.float64)
+    p0 = np.stack([r[1] for r in rows]).astype(np.float64)
+    return np.ascontiguousarray(p1), np.ascontiguousarray(p0)

@@ -9,8 +9,9 @@ import subprocess
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, ROOT, decode_fixture_paths, load_construction, load_decode, load_edge
-from oracle_lib import Port, awgn_llrs
+from conftest import (GOLDEN, ROOT, decode_fixture_paths, load_construction, load_decode, load_edge, load_p1,
+                      p1_fixture_paths)
+from oracle_lib import Port, awgn_llrs, awgn_probs, edge_probs
 
 pytestmark = pytest.mark.gpu
 
@@ -147,6 +148,45 @@ def test_gpu_wide_kernel_on_short_lists_and_edge_cases(torch_cuda, monkeypatch):
         assert [i for i in bad if i not in LATTICE_ROWS] == []
         got64 = pc.decode_batch_f64(llr.astype(np.float64), 64)
         assert np.array_equal(got64, want)
+
+
+@pytest.mark.parametrize("path", p1_fixture_paths(), ids=lambda p: p.split("p1_")[-1][:-4])
+def test_gpu_probability_domain_matches_golden(torch_cuda, path):
+    """decode_scl_p1 on the GPU against fixtures generated from the unmodified reference (ties, exact zeros,
+    the sigma == 0 branch and denormal inputs included): bit-exact, the arithmetic is the reference's."""
+    from polar_b200 import PolarCode
+    d = load_p1(path)
+    pc = PolarCode(d["n"], d["K"], 0.32, d["crc"])
+    got = pc.decode_p1_batch(d["p1"], d["p0"], d["L"])
+    assert pc.info(6) == -4
+    bad = [i for i in range(len(got)) if not np.array_equal(got[i], d["decoded"][i])]
+    assert bad == [], "rows differing from the reference: %s (first %d are edge rows)" % (bad, d["n_edge"])
+    # the reference-shaped single-codeword call
+    assert np.array_equal(pc.decode_scl_p1(d["p1"][-1], d["p0"][-1], d["L"]), d["decoded"][-1])
+
+
+@pytest.mark.parametrize("n,K,crc,L,B,eb", [(9, 256, 16, 4, 200, 1.0), (9, 256, 0, 32, 64, 1.0), (11, 1024, 16, 8, 16, 1.5),
+                                            (11, 1024, 0, 1, 64, 2.0), (8, 100, 7, 127, 12, 1.0), (7, 64, 8, 48, 64, 0.0),
+                                            (6, 20, 3, 5, 100, -1.0), (3, 4, 0, 9, 20, 0.0), (1, 1, 0, 2, 6, 0.0),
+                                            (12, 2048, 16, 2, 3, 2.0)])
+def test_gpu_probability_domain_matches_oracle(torch_cuda, n, K, crc, L, B, eb):
+    torch = torch_cuda
+    from polar_b200 import PolarCode, _lib, unpack_bits
+    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+    _, p1, p0 = awgn_probs(port, B, eb, seed=800 + n + L)
+    e1, e0 = edge_probs(1 << n, seed=n + 1)
+    p1, p0 = np.concatenate([e1, p1]), np.concatenate([e0, p0])
+    want = port.decode_p1_batch(p1, p0, L, nthreads=os.cpu_count() or 1)
+    got = pc.decode_p1_batch(p1, p0, L)
+    bad = [i for i in range(len(got)) if not np.array_equal(got[i], want[i])]
+    assert bad == [], "rows differing from the oracle: %s" % bad
+    # device-pointer entry point of the C ABI
+    d1, d0 = torch.from_numpy(p1).cuda(), torch.from_numpy(p0).cuda()
+    out = torch.zeros((len(p1), pc.KW), dtype=torch.int32, device="cuda")
+    rc = _lib.dev().polar_b200_decode_scl_p1(pc.ctx(len(p1)), d1.data_ptr(), d0.data_ptr(), len(p1), L, out.data_ptr(), None)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(unpack_bits(out.cpu().numpy().view(np.uint32), K), want)
 
 
 # rows of tests/golden/make_golden.py:edge_llrs whose LLRs sit on a lattice (+-40, integers, +-2): every

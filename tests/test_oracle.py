@@ -4,8 +4,9 @@ numpy lane-level model of the CUDA kernel's organisation against the port."""
 import numpy as np
 import pytest
 
-from conftest import CONSTRUCTIONS, decode_fixture_paths, load_construction, load_decode, load_edge
-from oracle_lib import Port, Ref, awgn_llrs, have_ref
+from conftest import (CONSTRUCTIONS, decode_fixture_paths, load_construction, load_decode, load_edge, load_p1,
+                      p1_fixture_paths)
+from oracle_lib import Port, Ref, awgn_llrs, awgn_probs, edge_probs, have_ref
 
 
 @pytest.mark.parametrize("n,K,crc", CONSTRUCTIONS)
@@ -52,6 +53,28 @@ def test_port_equals_compiled_reference(n, K, crc, L, B, eb):
     info, llr = awgn_llrs(port, B, eb, 4242 + n + L)
     assert np.array_equal(ref.encode(info), port.encode(info))
     assert np.array_equal(ref.decode_batch(llr, L, 8), port.decode_batch(llr, L, 8))
+
+
+@pytest.mark.parametrize("path", p1_fixture_paths(), ids=lambda p: p.split("p1_")[-1][:-4])
+def test_port_probability_domain_matches_golden(path):
+    """decode_scl_p1 (PolarCode.cpp:110-128, 375-420): the restatement against fixtures generated from the
+    unmodified reference, edge rows (ties, zeros, sigma == 0) included."""
+    d = load_p1(path)
+    got = Port(d["n"], d["K"], 0.32, d["crc"]).decode_p1_batch(d["p1"], d["p0"], d["L"], nthreads=8)
+    assert np.array_equal(got, d["decoded"])
+
+
+@pytest.mark.skipif(not have_ref(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("n,K,crc,L,B,eb", [(5, 16, 4, 4, 40, 1.0), (9, 256, 16, 32, 8, 1.5), (8, 100, 7, 127, 4, 1.0),
+                                            (7, 64, 0, 3, 40, 0.0), (3, 4, 0, 5, 20, 0.0), (10, 512, 8, 2, 8, 2.0)])
+def test_port_probability_domain_equals_compiled_reference(n, K, crc, L, B, eb):
+    ref, port = Ref(n, K, 0.32, crc), Port(n, K, 0.32, crc)
+    _, p1, p0 = awgn_probs(port, B, eb, seed=31 + n + L)
+    e1, e0 = edge_probs(1 << n, seed=n)
+    p1, p0 = np.concatenate([e1, p1]), np.concatenate([e0, p0])
+    want = np.stack([ref.decode_p1_one(p1[b], p0[b], L) for b in range(len(p1))])
+    assert np.array_equal(port.decode_p1_batch(p1, p0, L, nthreads=8), want)
+    assert np.array_equal(port.decode_p1_one(p1[-1], p0[-1], L), want[-1])
 
 
 def test_port_bler_harness_counts():
