@@ -209,6 +209,18 @@ __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
 #ifndef POLAR_PACKED
 #define POLAR_PACKED 1
 #endif
+#ifndef POLAR_TM_PIPE
+#define POLAR_TM_PIPE 1
+#endif
+#ifndef POLAR_SW_PIPE
+#define POLAR_SW_PIPE 1
+#endif
+#ifndef POLAR_X4_UNCOND
+#define POLAR_X4_UNCOND 1
+#endif
+#ifndef POLAR_TAIL_REGS
+#define POLAR_TAIL_REGS 1
+#endif
 __device__ __forceinline__ float sign_min(float a, float b) {
     return __int_as_float(__float_as_int(fminf(fabsf(a), fabsf(b))) |
                           ((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000));
@@ -277,6 +289,30 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
         float* dst = nullptr;
         if constexpr (!DST_TM) dst = xbase<C, LAM>(w) + w.lane;
         uint32_t word = 0;
+#if POLAR_TM_PIPE
+        if constexpr (!SRC_TM) {
+            // source rows are in the HBM/L2 scratch, destination is tensor memory: the loads of group i+1 are issued
+            // before group i is computed, so that their latency overlaps the MUFU work of the check nodes
+            float a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a[j] = src[j * 32]; b[j] = src[(j + M) * 32]; }
+#pragma unroll 1
+            for (int i0 = 0; i0 < M; i0 += 4) {
+                if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+                float na[4], nb[4], y[4];
+                const int nx = (i0 + 4 < M) ? i0 + 4 : i0;          // last group re-reads itself (harmless)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { na[j] = src[(nx + j) * 32]; nb[j] = src[(nx + j + M) * 32]; }
+                node4<ISG>(a, b, word, i0 & 31, y);
+                tm_st4(w.tm + i0, y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
+            }
+            tm_wait_st();
+            s.px = set_ptr(s.px, LAM - C::T, w.lane);
+            return;
+        }
+#endif
 #pragma unroll 1
         for (int i0 = 0; i0 < M; i0 += 4) {
             if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
@@ -367,7 +403,9 @@ __device__ __forceinline__ void layer_to_regs(const Warp& w, const Lane& s, Sub&
     constexpr int LAM = C::LB;
     const float* src = xbase<C, LAM - 1>(w) + get_ptr(s.px, LAM - 1 - C::T);
     const uint32_t field = s.sreg >> 15;                  // packed partial sums of layer NLOG-4
-    if (s.active) {
+    // POLAR_X4_UNCOND: idle lanes compute too (on don't-care rows of their own column), so that x4 is dead across
+    // the whole descent and its 16 registers are free for the prefetches up there
+    if (POLAR_X4_UNCOND || s.active) {
 #pragma unroll
         for (int j0 = 0; j0 < 16; j0 += 4) {
             float a[4], b[4];
@@ -447,21 +485,33 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
     float* dst = nullptr;
     if constexpr (!DST_TM) dst = xbase<C, T>(w) + w.lane;
     if (DST_TM || s.active) {                           // tcgen05.st is warp-collective
-#pragma unroll 1
-        for (int wd = 0; wd < MT / 32; ++wd) {
-            // partial-sum words of this path for the g levels: level lev, local element i sits at
-            // position beta + MT * brev(i) of layer lev; flat index (1 << (T - lev)) + i
-            uint32_t sw[1 << T];
+        // partial-sum words of this path for the g levels: level lev, local element i sits at
+        // position beta + MT * brev(i) of layer lev; flat index (1 << (T - lev)) + i
+        uint32_t sw[1 << T] = {};
+        auto load_sw = [&](int wd, uint32_t (&dstw)[1 << T]) {
             static_for<S0 + 1, T + 1>([&](auto lev_c) {
                 constexpr int lev = decltype(lev_c)::value;
                 if constexpr ((NODE >> (T - lev)) & 1) {
                     const uint32_t* base = sbase<C, lev>(w) + get_ptr(s.ps, lev - 1);
                     static_for<0, (1 << (T - lev))>([&](auto i_c) {
                         constexpr int i = decltype(i_c)::value;
-                        sw[(1 << (T - lev)) + i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
+                        dstw[(1 << (T - lev)) + i] = base[(wd + (MT / 32) * (int)cbrev(i, T - lev)) * 32];
                     });
                 }
             });
+        };
+#if POLAR_SW_PIPE
+        load_sw(0, sw);
+#endif
+#pragma unroll 1
+        for (int wd = 0; wd < MT / 32; ++wd) {
+#if POLAR_SW_PIPE
+            // the words of the next 32 betas are requested now (most of them come from the L2-resident scratch)
+            uint32_t swn[1 << T] = {};
+            load_sw(wd + 1 < MT / 32 ? wd + 1 : wd, swn);
+#else
+            load_sw(wd, sw);
+#endif
             // two betas at a time (wd * 32 + bi and + 1), so that every check node has a partner for the packed pipe
             auto compute_pair = [&](int bi, float (&v)[2][CNT]) {
                 static_for<S0 + 1, T + 1>([&](auto lev_c) {
@@ -491,6 +541,9 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                 top_load_pair<C, NODE, 0>(w, wd * 32 + ((bi + 4) & 31), va);   // wraps harmlessly
                 compute_pair(bi + 2, vb);
             }
+#if POLAR_SW_PIPE
+            static_for<0, (1 << T)>([&](auto i_c) { sw[decltype(i_c)::value] = swn[decltype(i_c)::value]; });
+#endif
         }
         if constexpr (DST_TM) tm_wait_st();
     }
@@ -962,10 +1015,66 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
 
         // ---- u-hat = packed polar transform of the re-encoded codeword (partial-sum layer 0) ----
         uint32_t* D = sbase<C, 0>(w) + lane;
+        bool pass = true;
+#if POLAR_TAIL_REGS
+        {
+            // chunks of up to 32 words are transformed in registers (the subtree registers are dead here): every
+            // chunk is 32 independent loads, not a chain of read-modify-writes through L2
+            constexpr int CH = NW < 32 ? NW : 32;
+            for (int sw = NW >> 1; sw >= CH; sw >>= 1) {              // strides between chunks (N > 1024 only)
+#pragma unroll 1
+                for (int i0 = 0; i0 < NW; i0 += 8) {
+                    if (i0 & sw) continue;
+                    uint32_t lo[8], hi[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { lo[j] = D[(i0 + j) * 32]; hi[j] = D[(i0 + j + sw) * 32]; }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) D[(i0 + j) * 32] = lo[j] ^ hi[j];
+                }
+            }
+            unsigned long long odd = 0ull;                            // parity rows with an odd sum so far
+            const int crc_fast = a.crc < 64 ? a.crc : 64;
+#pragma unroll 1
+            for (int base = 0; base < NW; base += CH) {
+                uint32_t x[CH];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) x[i] = D[(base + i) * 32];
+#pragma unroll
+                for (int sw = CH >> 1; sw >= 1; sw >>= 1)
+#pragma unroll
+                    for (int i = 0; i < CH; ++i)
+                        if ((i & sw) == 0) x[i] ^= x[i + sw];
+#pragma unroll
+                for (int i = 0; i < CH; ++i) {
+                    uint32_t v = x[i];
+                    v ^= (v >> 16) & 0x0000FFFFu;
+                    v ^= (v >> 8) & 0x00FF00FFu;
+                    v ^= (v >> 4) & 0x0F0F0F0Fu;
+                    v ^= (v >> 2) & 0x33333333u;
+                    v ^= (v >> 1) & 0x55555555u;
+                    x[i] = v;
+                    D[(base + i) * 32] = v;
+                }
+#pragma unroll 1
+                for (int r = 0; r < crc_fast; ++r) {                  // PolarCode.cpp:93-108
+                    const uint32_t* m = a.crc_masks + r * NW + base;
+                    uint32_t acc = 0;
+#pragma unroll
+                    for (int i = 0; i < CH; ++i) acc ^= x[i] & m[i];
+                    odd ^= (unsigned long long)(__popc(acc) & 1) << r;
+                }
+            }
+            if (odd) pass = false;
+            for (int r = 64; r < a.crc; ++r) {                        // more than 64 parity rows: from memory
+                uint32_t acc = 0;
+                for (int i = 0; i < NW; ++i) acc ^= D[i * 32] & a.crc_masks[r * NW + i];
+                if (__popc(acc) & 1) pass = false;
+            }
+        }
+#else
         for (int sw = NW >> 1; sw >= 1; sw >>= 1)
             for (int i = 0; i < NW; ++i)
                 if ((i & sw) == 0) D[i * 32] ^= D[(i + sw) * 32];
-        bool pass = true;
         for (int i = 0; i < NW; ++i) {
             uint32_t x = D[i * 32];
             x ^= (x >> 16) & 0x0000FFFFu;
@@ -980,6 +1089,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             for (int i = 0; i < NW; ++i) acc ^= D[i * 32] & a.crc_masks[r * NW + i];
             if (__popc(acc) & 1) pass = false;
         }
+#endif
         // ---- final pick, PolarCode.cpp:609-644 ----
         const unsigned act = gballot<W>(s.active, gbase);
         const unsigned passm = gballot<W>(s.active && pass, gbase);
@@ -997,6 +1107,32 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             const int wl = g * W + __shfl_sync(FULL_MASK, win, g * W);
             const bool wa = __shfl_sync(FULL_MASK, (int)win_active, g * W);
             const uint32_t* U = sbase<C, 0>(w) + wl;
+#if POLAR_TAIL_REGS
+            // the winner's u-hat spread over the lanes (word 32 q + lane in uw[q]); a bit lookup is then a shuffle,
+            // not a second dependent trip to L2
+            constexpr int NR = (NW + 31) / 32;
+            uint32_t uw[NR];
+#pragma unroll
+            for (int q = 0; q < NR; ++q) uw[q] = (32 * q + lane < NW) ? U[(32 * q + lane) * 32] : 0u;
+            for (int t0 = 0; t0 < KW; t0 += 32) {           // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
+                const int t = t0 + lane;
+                const int jmax = (t < KW) ? min(32, a.K - 32 * t) : 0;
+                uint32_t word = 0;
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const int pos = (i < jmax) ? (int)a.info_order[32 * t + i] : 0;
+                    const int wi = pos >> 5;
+                    uint32_t v = __shfl_sync(FULL_MASK, uw[0], wi & 31);
+#pragma unroll
+                    for (int q = 1; q < NR; ++q) {
+                        const uint32_t vq = __shfl_sync(FULL_MASK, uw[q], wi & 31);
+                        if ((wi >> 5) == q) v = vq;
+                    }
+                    if (i < jmax) word |= ((v >> (pos & 31)) & 1u) << i;
+                }
+                if (t < KW) a.out[(size_t)cwg * KW + t] = wa ? word : 0u;
+            }
+#else
             for (int t = lane; t < KW; t += 32) {           // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
                 uint32_t word = 0;
                 if (wa) {
@@ -1008,6 +1144,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 }
                 a.out[(size_t)cwg * KW + t] = word;
             }
+#endif
         }
         __syncwarp();
     }
