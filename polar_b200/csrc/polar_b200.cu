@@ -1161,10 +1161,31 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
     if (fv2 != fv) { fv = fv2; chunk = chunk_size(round_size(fv)); }
     int nchunks = (int)((B + chunk - 1) / chunk);
     if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
+    // chunk boundaries (in codewords). Equal chunks by default. With one codeword per warp (lists 17..32) decoding a
+    // round takes several times longer than copying it in, so the chunks grow geometrically instead (1, 4, 16, ...
+    // rounds): only the first, small copy is exposed, and there are fewer chunk boundaries, each of which is a
+    // grid-wide join where the fastest warps wait for the slowest.
+    long long bounds[polar_b200_ctx::kMaxChunks + 1];
+    bounds[0] = 0;
+    const bool geometric = fv >= 0 && kFastVariants[fv].wlog == 5 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1;
+    if (geometric) {
+        const long long per_round = round_size(fv);
+        long long rounds_in_chunk = 1;
+        nchunks = 0;
+        while (bounds[nchunks] < B && nchunks < polar_b200_ctx::kMaxChunks) {
+            long long hi = bounds[nchunks] + rounds_in_chunk * per_round;
+            if (hi > B || nchunks == polar_b200_ctx::kMaxChunks - 1) hi = B;
+            if (B - hi < per_round * rounds_in_chunk / 2) hi = B;       // no small leftover chunk
+            bounds[++nchunks] = hi;
+            rounds_in_chunk *= 4;
+        }
+    } else {
+        for (int i = 1; i <= nchunks; ++i) bounds[i] = ((long long)i * chunk < B) ? (long long)i * chunk : B;
+    }
     c->last_chunks = nchunks;
     for (int i = 0; i < nchunks; ++i) {
-        const long long lo = (long long)i * chunk;
-        const int nb = (int)((lo + chunk <= B) ? chunk : (B - lo));
+        const long long lo = bounds[i];
+        const int nb = (int)(bounds[i + 1] - lo);
         float* d_in = c->d_llr_stage + (size_t)lo * c->N;
         uint32_t* d_o = c->d_out_stage + (size_t)lo * c->KW;
         CU_TRY(cudaMemcpyAsync(d_in, llr_host + (size_t)lo * c->N, (size_t)nb * c->N * sizeof(float),

@@ -34,6 +34,11 @@ namespace fast {
 #define POLAR_LDCHAN(p) __ldg(p)
 #endif
 
+// lists with at least this many codewords per warp stage their channel LLRs / XS arrays transposed (0 = never)
+#ifndef POLAR_TRANSPOSED_MIN_G
+#define POLAR_TRANSPOSED_MIN_G 16
+#endif
+
 template <int NLOG_, int T_, int LAMS_, int WLOG_ = 5, int SGMIN_ = 16, int TM_ = 0>
 struct Cfg {
     static constexpr int NLOG = NLOG_, T = T_, LAMS = LAMS_, WLOG = WLOG_;
@@ -75,7 +80,14 @@ struct Cfg {
     static constexpr int SS_ROWS = ss_rows();
     static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64;
     static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
-    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + (size_t)G * XS_FLOATS + PA_FLOATS;
+    // lists <= 16 (G > 1 codewords per warp): the channel LLRs of the warp's codewords are staged TRANSPOSED
+    // ([position / 4][codeword][4], so that a lane still reads float4) behind the XS arrays, which are stored
+    // [index][codeword]
+    static constexpr bool TRANSPOSED = POLAR_TRANSPOSED_MIN_G > 1 && G >= POLAR_TRANSPOSED_MIN_G;
+    static constexpr int CHT_FLOATS = TRANSPOSED ? G * N : 0;
+    static constexpr size_t XST_OFF = (size_t)GX_ROWS * 32;                       // XS arrays (compact per codeword, or transposed)
+    static constexpr size_t CHT_OFF = XST_OFF + (size_t)G * XS_FLOATS + PA_FLOATS;
+    static constexpr size_t GX_FLOATS = (size_t)GX_ROWS * 32 + (size_t)G * XS_FLOATS + PA_FLOATS + CHT_FLOATS;
     static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
 };
 
@@ -102,6 +114,9 @@ struct Warp {          // per-warp pointers
     const float* chan; // channel LLRs of THIS LANE's codeword
     uint32_t tm;       // TMEM address of this warp's quadrant (TM configurations)
     int lane;
+    float* xst;        // lists <= 16: XS arrays of the warp's codewords, transposed [index][codeword]
+    float* cht;        // lists <= 16: channel LLRs of the warp's codewords, transposed [position][codeword]
+    int g;             // lists <= 16: this lane's codeword within the warp
 };
 
 struct Lane {          // per-path state
@@ -456,6 +471,27 @@ __device__ __forceinline__ void top_load_pair(const Warp& w, int q0, float (&v)[
     constexpr int T = C::T, MT = C::MT, BITS = C::NLOG - T;
     constexpr int S0 = lead_zeros(NODE, T);
     constexpr int CNT = 1 << (T - S0);
+    if constexpr (C::TRANSPOSED) {
+        // several codewords per warp: transposed staging, lanes of different codewords read neighbouring words
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int c = 2 * H + p;
+            if constexpr (S0 == 0) {
+                const float4* src = reinterpret_cast<const float4*>(w.cht) +
+                                    ((size_t)(CNT / 4) * (brev_bits(q0, BITS) + (cbrev(c, 2) << (BITS - 2)))) * C::G + w.g;
+#pragma unroll
+                for (int q = 0; q < CNT / 4; ++q) {
+                    const float4 t4 = src[q * C::G];
+                    v[p][4 * q] = t4.x; v[p][4 * q + 1] = t4.y; v[p][4 * q + 2] = t4.z; v[p][4 * q + 3] = t4.w;
+                }
+            } else {
+                const float* src = w.xst + (size_t)(C::xs_off(S0) + q0 + c) * C::G + w.g;
+#pragma unroll
+                for (int i = 0; i < CNT; ++i) v[p][i] = src[(MT * (int)cbrev(i, T - S0)) * C::G];
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int c = 2 * H + p;
@@ -587,6 +623,81 @@ __device__ __forceinline__ void top_solo_publish_tm(const Warp& w) {
         tm_wait_st();
     }
 }
+// ---- lists <= 16: stage the channel LLRs of the warp's G codewords transposed, then node 0 of layer T (and the
+// compact arrays XS_1..XS_T, transposed too) with lane = (codeword, residue of beta mod W). `first` = channel row of
+// the warp's first codeword, `last_g` = last valid codeword of the warp (rows beyond the batch repeat it).
+template <class C>
+__device__ __noinline__ void top_solo_transposed(const Warp w, const float* first, int last_g, int c0) {
+    constexpr int T = C::T, N = C::N, NLOG = C::NLOG, G = C::G, W = C::W, MT = C::MT;
+    const int lane = w.lane, g = w.g, slot = lane & (W - 1);
+    // channel rows (coalesced float4 reads) -> [position / 4][codeword][4]: every lane writes whole 128-byte lines
+    float4* cht4 = reinterpret_cast<float4*>(w.cht);
+    constexpr int GB = G < 16 ? G : 16;               // codewords per batch of loads (all issued before the first store)
+#pragma unroll 1
+    for (int j0 = 0; j0 < N / 4; j0 += 32) {
+#pragma unroll 1
+        for (int q0 = 0; q0 < G; q0 += GB) {
+            float4 v[GB];
+#pragma unroll
+            for (int q = 0; q < GB; ++q)
+                v[q] = POLAR_LDCHAN(reinterpret_cast<const float4*>(first + (size_t)(q0 + q < last_g ? q0 + q : last_g) * N) + j0 + lane);
+#pragma unroll
+            for (int q = 0; q < GB; ++q) cht4[(size_t)(j0 + lane) * G + q0 + q] = v[q];
+        }
+    }
+    __syncwarp();
+    // XS_1[brev(k)] = f(chan[2k], chan[2k+1]) (PolarCode.cpp:438-446): one float4 = two check nodes (packed pipe).
+    // Loads are issued in batches of four so that their latency overlaps (the stores may alias for the compiler).
+    {
+        float* xs1 = w.xst + (size_t)C::xs_off(1) * G + g;
+        static_assert((N / 4) % (4 * W) == 0, "whole batches");
+#pragma unroll 1
+        for (int j = slot; j < N / 4; j += 4 * W) {
+            float4 c[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) c[q] = cht4[(size_t)(j + q * W) * G + g];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float y0, y1;
+                f_rule2(c[q].x, c[q].y, c[q].z, c[q].w, y0, y1);
+                xs1[(size_t)brev_bits(2 * (j + q * W), NLOG - 1) * G] = y0;
+                xs1[(size_t)brev_bits(2 * (j + q * W) + 1, NLOG - 1) * G] = y1;
+            }
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int lev = 2; lev <= T; ++lev) {
+        const float* in = w.xst + (size_t)C::xs_off(lev - 1) * G + g;
+        float* out = w.xst + (size_t)C::xs_off(lev) * G + g;
+        const int M = N >> lev;
+#pragma unroll 1
+        for (int b = slot; b < M; b += 4 * W) {
+            float x[4], y[4], z[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { x[q] = in[(size_t)(b + q * W) * G]; y[q] = in[(size_t)(b + q * W + M) * G]; }
+            f_rule2(x[0], y[0], x[1], y[1], z[0], z[1]);
+            f_rule2(x[2], y[2], x[3], y[3], z[2], z[3]);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[(size_t)(b + q * W) * G] = z[q];
+        }
+        __syncwarp();
+    }
+    const float* xt = w.xst + (size_t)C::xs_off(T) * G + g;
+    if constexpr (C::TM && C::LT == T) {
+        // layer T in tensor memory: every lane stores its own codeword's XS_T rows into its column
+        for (int b = 0; b < MT; b += 4) {
+            const float v[4] = {xt[(size_t)b * G], xt[(size_t)(b + 1) * G], xt[(size_t)(b + 2) * G], xt[(size_t)(b + 3) * G]};
+            tm_st4(w.tm + b, v);
+        }
+        tm_wait_st();
+    } else {
+        float* col = xbase<C, T>(w) + (lane & ~(W - 1)) + c0;
+        for (int b = slot; b < MT; b += W) col[b * 32] = xt[(size_t)b * G];
+        __syncwarp();
+    }
+}
+
 // all codewords of the warp, one after the other (c0 = local index of the first path)
 template <class C>
 __device__ __forceinline__ void top_solo(const Warp& w, int c0, bool valid) {
@@ -676,7 +787,8 @@ __device__ __noinline__ float phase_a(const Warp w, int PA, int c0) {
 // refresh everything above the register subtree for the 16-leaf block starting at phi0, ending with
 // the 16 LLRs of layer NLOG-4 in registers (PolarCode.cpp:422-455 for the layers involved)
 template <class C>
-__device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, int phi0, int c0, bool valid) {
+__device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, int phi0, int c0, bool valid,
+                                              const float* first_row, int last_g) {
     constexpr int T = C::T, NLOG = C::NLOG, LB = C::LB;
     const int lam_top = (phi0 == 0) ? 0 : NLOG - (__ffs(phi0) - 1);      // <= LB
     bool first = true;
@@ -684,7 +796,11 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
     if (lam_top <= T) {
         const int node = phi0 >> (NLOG - T);
         switch (node) {
-            case 0: top_solo<C>(w, c0, valid); s.px = set_ptr(s.px, 0, (w.lane & ~(C::W - 1)) + c0); break;
+            case 0:
+                if constexpr (C::TRANSPOSED) top_solo_transposed<C>(w, first_row, last_g, c0);
+                else top_solo<C>(w, c0, valid);
+                s.px = set_ptr(s.px, 0, (w.lane & ~(C::W - 1)) + c0);
+                break;
 #define POLAR_TN(N_) case N_: if constexpr (N_ < (1 << T)) top_node<C, N_>(w, s); break;
             POLAR_TN(1) POLAR_TN(2) POLAR_TN(3) POLAR_TN(4) POLAR_TN(5) POLAR_TN(6) POLAR_TN(7)
             POLAR_TN(8) POLAR_TN(9) POLAR_TN(10) POLAR_TN(11) POLAR_TN(12) POLAR_TN(13) POLAR_TN(14) POLAR_TN(15)
@@ -926,7 +1042,10 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     }
     const int gbase = lane & ~(W - 1), slot = lane & (W - 1), grp_in_warp = lane / W;
     w.gx = a.gx + C::GX_FLOATS * gwarp;
-    w.xs = w.gx + (size_t)C::GX_ROWS * 32 + (size_t)grp_in_warp * C::XS_FLOATS;
+    w.xs = w.gx + C::XST_OFF + (size_t)grp_in_warp * C::XS_FLOATS;
+    w.xst = w.gx + C::XST_OFF;
+    w.cht = w.gx + C::CHT_OFF;
+    w.g = grp_in_warp;
     w.gs = a.gs + C::GS_WORDS * gwarp;
     const int L = a.L, KW = (a.K + 31) >> 5;
     const int c0 = L - 1;                          // first path popped from the free stack (PolarCode.cpp:250-263)
@@ -945,6 +1064,8 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         const int cw = grp * G + grp_in_warp;
         const bool valid = cw < a.B;
         w.chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
+        const float* first_row = a.llr + (size_t)grp * G * N;     // the warp's codewords are consecutive rows
+        const int last_g = (a.B - 1 - grp * G) < (G - 1) ? (a.B - 1 - grp * G) : (G - 1);
         Lane s;
         s.active = valid && (slot == c0);
         s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0;
@@ -973,7 +1094,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         }
 #pragma unroll 1
         for (int phi0 = (W == 32 ? a.PA : 0); phi0 < N; phi0 += 16) {
-            if (!have_x4) descend_block<C>(w, s, r, phi0, c0, valid);
+            if (!have_x4) descend_block<C>(w, s, r, phi0, c0, valid, first_row, last_g);
             have_x4 = false;
             const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
 #pragma unroll 1

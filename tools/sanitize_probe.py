@@ -16,4 +16,19 @@ for (n,K,crc,L,B) in [(9,256,16,32,6),(9,256,16,4,19),(9,256,0,16,5),(11,1024,16
     same = np.array_equal(got, want) and np.array_equal(g64, want)
     ok &= same
     print(n, K, crc, L, B, "kernel kind", pc.info(6), "ok" if same else "MISMATCH", flush=True)
+# wide-list kernel (lists 33..127, fp32 and f64) and the probability-domain decoder
+from oracle_lib import awgn_probs
+for (n,K,crc,L,B) in [(9,256,16,40,3),(7,64,8,100,5),(9,256,0,64,2)]:
+    port = Port(n,K,0.32,crc); pc = PolarCode(n,K,0.32,crc)
+    info, llr = awgn_llrs(port, B, 1.0, 6)
+    want = port.decode_batch(llr, L)
+    same = np.array_equal(pc.decode_batch(llr, L), want) and np.array_equal(pc.decode_batch_f64(llr.astype(np.float64), L), want)
+    ok &= same
+    print(n, K, crc, L, B, "kernel kind", pc.info(6), "ok" if same else "MISMATCH", flush=True)
+for (n,K,crc,L,B) in [(9,256,16,8,4),(7,64,8,48,5),(8,100,7,127,2)]:
+    port = Port(n,K,0.32,crc); pc = PolarCode(n,K,0.32,crc)
+    info, p1, p0 = awgn_probs(port, B, 1.0, 7)
+    same = np.array_equal(pc.decode_p1_batch(p1, p0, L), port.decode_p1_batch(p1, p0, L))
+    ok &= same
+    print(n, K, crc, L, B, "p1 kernel kind", pc.info(6), "ok" if same else "MISMATCH", flush=True)
 print("ALL OK" if ok else "FAIL")
