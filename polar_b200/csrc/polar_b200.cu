@@ -1159,6 +1159,15 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
     long long chunk = chunk_size(round_size(fv));
     const int fv2 = pick_fast_variant(c, L, (int)chunk);
     if (fv2 != fv) { fv = fv2; chunk = chunk_size(round_size(fv)); }
+    if (fv >= 0 && kFastVariants[fv].wlog <= 1 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1) {
+        // lists <= 2 decode at least twice as fast as PCIe delivers the LLRs (8 KB per codeword at N = 2048): the copy is the
+        // critical path, so cut the batch into six equal chunks even if that is less than one round of the grid --
+        // only the last chunk's decode is then exposed
+        fv = pick_fast_variant(c, L, (B + 5) / 6);
+        const int cpb = kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);     // codewords per block
+        chunk = (((long long)(B + 5) / 6 + cpb - 1) / cpb) * cpb;
+        if (chunk > B) chunk = B;
+    }
     int nchunks = (int)((B + chunk - 1) / chunk);
     if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
     // chunk boundaries (in codewords). Equal chunks by default. With one codeword per warp (lists 17..32) decoding a

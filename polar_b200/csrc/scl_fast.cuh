@@ -850,6 +850,11 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     // keep the L best forks under (metric asc, fork index asc). Metrics are >= 0: uint order = float order.
     const unsigned klo = __float_as_uint(mlo), khi = __float_as_uint(mhi);
     const bool like1 = m1 < m0;                            // likely fork is bit 1
+    if constexpr (W == 1) {
+        // plain SC (list 1): the better of the two forks survives, fork 0 on a tie (index order, PolarCode.cpp:543-553)
+        if (s.active) s.pm = like1 ? m1 : m0;
+        return like1 ? 1u : 0u;
+    }
     if constexpr (W == 32) {
         if (2 * A > L) {
             if (A == L) {
