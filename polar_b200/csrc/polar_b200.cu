@@ -779,6 +779,22 @@ const FastVariant kFastVariants[] = {
     POLAR_FAST(8, 3, 3, 5, 16, 1),     // 32: N=256 lists 17..32
     // alternates (POLAR_B200_FAST_VARIANT=<index>)
     POLAR_FAST(11, 3, 6, 5, 20, 1),    // 33: N=2048 lists 17..32 without tensor memory, 20 warps/SM
+    // other block lengths, lists 1..16 (2..32 codewords per warp), same placement as their list-32 entries
+    POLAR_FAST_TM(10, 3, 5, 4, 4, 4),  // 34: N=1024 lists 9..16
+    POLAR_FAST_TM(10, 3, 5, 3, 4, 4),
+    POLAR_FAST_TM(10, 3, 5, 2, 4, 4),
+    POLAR_FAST_TM(10, 3, 5, 1, 4, 4),
+    POLAR_FAST_TM(10, 3, 5, 0, 4, 4),
+    POLAR_FAST_TM(12, 3, 6, 4, 4, 4),  // 39: N=4096 lists 9..16
+    POLAR_FAST_TM(12, 3, 6, 3, 4, 4),
+    POLAR_FAST_TM(12, 3, 6, 2, 4, 4),
+    POLAR_FAST_TM(12, 3, 6, 1, 4, 4),
+    POLAR_FAST_TM(12, 3, 6, 0, 4, 4),
+    POLAR_FAST(8, 3, 3, 4, 4, 4),      // 44: N=256 lists 9..16
+    POLAR_FAST(8, 3, 3, 3, 4, 4),
+    POLAR_FAST(8, 3, 3, 2, 4, 4),
+    POLAR_FAST(8, 3, 3, 1, 4, 4),
+    POLAR_FAST(8, 3, 3, 0, 4, 4),
 };
 constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
@@ -847,7 +863,7 @@ int decode_wide_w(polar_b200_ctx* c, const typename Dom::Real* in0, const typena
     const int n = c->n, elem = (int)sizeof(Val);
     const int blocks_per_sm = env_int("POLAR_B200_WIDE_BPS", 1024 / W >= 8 ? 8 : 4);
     const int budget = (200 * 1024) / blocks_per_sm;
-    const int fixed = W * (2 * (int)sizeof(Real) + 32 + 12) + (16 + 2 * (int)sizeof(Real)) * (W / 32);
+    const int fixed = W * (2 * (int)sizeof(Real) + 32 + 12) + (16 + 4 * (int)sizeof(Real)) * (W / 32);
     auto s_rows_from = [&](int lam0) { int sr = 0; for (int lam = (lam0 < 1 ? 1 : lam0); lam <= n - 1; ++lam) sr += ((1 << (n - lam)) + 31) / 32; return sr; };
     int lamS = n;
     while (lamS > 1) {

@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Dom> a) {
     Val* sx = reinterpret_cast<Val*>(smem_raw);
     unsigned char* p = smem_raw + (size_t)a.smem_x_rows * W * sizeof(Val);
     Real* red = reinterpret_cast<Real*>(p); p += 2 * NWARP * sizeof(Real);   // block-max scratch, double-buffered
+    Real* r_lo = reinterpret_cast<Real*>(p); p += NWARP * sizeof(Real);      // per-warp worst likely / best unlikely fork
+    Real* r_hi = reinterpret_cast<Real*>(p); p += NWARP * sizeof(Real);
     Real* x_m0 = reinterpret_cast<Real*>(p); p += W * sizeof(Real);
     Real* x_m1 = reinterpret_cast<Real*>(p); p += W * sizeof(Real);
     unsigned long long* x_plo = reinterpret_cast<unsigned long long*>(p); p += W * 8;   // staged px.lo, px.hi, ps.lo, ps.hi
@@ -247,9 +249,28 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Dom> a) {
                 x_plo[tid] = px.lo; x_phi[tid] = px.hi; x_slo[tid] = ps.lo; x_shi[tid] = ps.hi; x_sn[tid] = s_n;
                 srcof[tid] = tid;
                 const uint32_t ab = __ballot_sync(FULL_MASK, active);
-                if (lane == 0) b_act[warp] = ab;
+                {
+                    // per-warp worst likely and best unlikely fork, for the common exit below
+                    Real wl = active ? rmin<Real>(m0, m1) : -Arith<Real>::inf();
+                    Real bu = active ? rmax<Real>(m0, m1) : Arith<Real>::inf();
+                    for (int o = 16; o > 0; o >>= 1) {
+                        wl = rmax<Real>(wl, __shfl_xor_sync(FULL_MASK, wl, o));
+                        bu = rmin<Real>(bu, __shfl_xor_sync(FULL_MASK, bu, o));
+                    }
+                    if (lane == 0) { b_act[warp] = ab; r_lo[warp] = wl; r_hi[warp] = bu; }
+                }
                 __syncthreads();
                 const int A = total(b_act);
+                if (A == L) {
+                    // common exit (block-uniform): the list is full and every unlikely fork is strictly worse than
+                    // every likely fork, so each path keeps its likely fork; nothing is killed or cloned
+                    Real wl = r_lo[0], bu = r_hi[0];
+                    for (int w = 1; w < NWARP; ++w) { wl = rmax<Real>(wl, r_lo[w]); bu = rmin<Real>(bu, r_hi[w]); }
+                    if (bu > wl) {
+                        if (active) { u = (m1 < m0) ? 1u : 0u; pm = rmin<Real>(m0, m1); }
+                        goto leaf_done;
+                    }
+                }
                 bool keep0 = active, keep1 = active;
                 if (2 * A > L && active) {
                     // keep the rho = L best of the 2A forks under (metric asc, fork index asc)
@@ -300,6 +321,7 @@ __global__ void __launch_bounds__(W) scl_wide_kernel(const Args<Dom> a) {
                 }
             }
 
+        leaf_done:
             // ---- partial sums (PolarCode.cpp:457-473), bit-packed, butterfly order ----
             if ((phi & 1) == 0) {
                 s_n = u;

@@ -65,6 +65,19 @@ PARITY = [
     (10, 512, 16, 32, 40, 1.5),      # N = 1024
     (8, 128, 8, 32, 80, 1.5),        # N = 256
     (12, 2048, 16, 8, 48, 1.5),
+    (10, 512, 16, 1, 300, 2.0),      # other block lengths on the several-codewords-per-warp variants (lists 1..16)
+    (10, 512, 16, 4, 200, 1.5),
+    (10, 512, 0, 16, 70, 1.5),
+    (12, 2048, 0, 1, 100, 2.0),
+    (12, 2048, 16, 2, 70, 1.5),
+    (12, 2048, 16, 13, 20, 1.5),
+    (8, 128, 8, 1, 500, 2.0),
+    (8, 128, 8, 4, 300, 1.0),
+    (8, 128, 0, 16, 130, 1.0),
+    (11, 1024, 16, 1, 2000, 1.0),    # list 1 / 2 with parity bits, low SNR (transposed staging, ragged batch)
+    (11, 1024, 16, 2, 999, 1.0),
+    (9, 256, 16, 1, 4099, 1.0),
+    (9, 256, 0, 2, 1030, 1.0),
     (7, 64, 8, 3, 333, 0.5),         # list size not a power of two, ragged batch
     (6, 20, 3, 5, 257, -1.0),
     (5, 16, 4, 16, 100, 0.0),
