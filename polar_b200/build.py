@@ -19,8 +19,9 @@ INC = os.path.join(ROOT, "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC,
+    "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC,
 ]
+FAST_PARTS = 4          # fast_parts.cu is compiled once per quarter of the variant table (fast_variants.cuh)
 
 
 def _nvcc():
@@ -37,20 +38,40 @@ def _stale(target, sources):
     return any(os.path.getmtime(s) > t for s in sources)
 
 
-def build(force=False, verbose=False):
-    os.makedirs(LIB, exist_ok=True)
+def build(force=False, verbose=False, out_dir=None, extra_flags=()):
+    """Compile the CUDA translation units in parallel (polar_b200.cu + fast_parts.cu x FAST_PARTS), link
+    libpolar_b200.so, then libpolar_host.so. `out_dir` / `extra_flags` build a variant of the libraries elsewhere
+    (A/B runs: POLAR_B200_LIB_DIR)."""
+    lib = out_dir or LIB
+    obj = os.path.join(lib, "obj")
+    os.makedirs(obj, exist_ok=True)
     hdrs = [os.path.join(INC, "polar_b200.h")] + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
                                                    if f.endswith((".h", ".cuh"))]
-    dev_so = os.path.join(LIB, "libpolar_b200.so")
-    dev_src = [os.path.join(CSRC, "polar_b200.cu")]
+    dev_so = os.path.join(lib, "libpolar_b200.so")
+    dev_src = [os.path.join(CSRC, "polar_b200.cu"), os.path.join(CSRC, "fast_parts.cu")]
     if force or _stale(dev_so, dev_src + hdrs):
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + dev_src + ["-o", dev_so]
-        subprocess.check_call(cmd)
-    host_so = os.path.join(LIB, "libpolar_host.so")
+        flags = NVCC_FLAGS + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+        jobs = [([_nvcc()] + flags + ["-c", dev_src[0], "-o", os.path.join(obj, "polar_b200.o")], "polar_b200.cu")]
+        for k in range(FAST_PARTS):
+            jobs.append(([_nvcc()] + flags + ["-DPOLAR_PART=%d" % k, "-c", dev_src[1], "-o", os.path.join(obj, "fast_part%d.o" % k)],
+                         "fast_parts.cu part %d" % k))
+        procs = [(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), name) for cmd, name in jobs]
+        failed = []
+        for pr, name in procs:
+            out, _ = pr.communicate()
+            if verbose or pr.returncode != 0:
+                sys.stdout.write(out)
+            if pr.returncode != 0:
+                failed.append(name)
+        if failed:
+            raise RuntimeError("nvcc failed for: " + ", ".join(failed))
+        objs = [os.path.join(obj, "polar_b200.o")] + [os.path.join(obj, "fast_part%d.o" % k) for k in range(FAST_PARTS)]
+        subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", dev_so])
+    host_so = os.path.join(lib, "libpolar_host.so")
     host_src = [os.path.join(CSRC, "PolarCode.cpp")]
     if force or _stale(host_so, host_src + hdrs + [dev_so]):
         cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-I" + INC, "-I" + CSRC] + host_src + [
-            "-L" + LIB, "-lpolar_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-o", host_so]
+            "-L" + lib, "-lpolar_b200", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-o", host_so]
         subprocess.check_call(cmd)
     return dev_so, host_so
 
@@ -81,6 +102,14 @@ def build_acceptance(ref_dir="/root/reference/PolarC"):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
-    build_acceptance()
-    print("built:", os.listdir(LIB))
+    # python -m polar_b200.build [--force] [-v] [--dir <name under polar_b200/>] [-- extra nvcc flags]
+    argv = sys.argv[1:]
+    extra = []
+    if "--" in argv:
+        extra = argv[argv.index("--") + 1:]
+        argv = argv[:argv.index("--")]
+    out_dir = os.path.join(PKG, argv[argv.index("--dir") + 1]) if "--dir" in argv else None
+    build(force="--force" in argv, verbose="-v" in argv, out_dir=out_dir, extra_flags=extra)
+    if out_dir is None:
+        build_acceptance()
+    print("built:", sorted(f for f in os.listdir(out_dir or LIB) if f.endswith(".so")))

@@ -38,118 +38,8 @@
 
 #include "polar_b200.h"
 
-#define FULL_MASK 0xffffffffu
-
-namespace {
-
-constexpr int kMaxList = 127;       // the reference's own limit (uint8_t loop counters, PolarCode.cpp:497-605)
-constexpr int kMaxN = 13;          // log2 block length supported by the pointer packing (12 x 5 bits)
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-template <class Real>
-struct DecodeArgsT {
-    const Real* llr;             // [B][N]
-    uint32_t* out;               // [B][KW]
-    const uint32_t* frozen_words;// [max(1,N/32)], bit phi set = frozen
-    const uint16_t* info_order;  // [K + crc]
-    const uint32_t* crc_masks;   // [crc][NW] over phi
-    Real* gx;                    // per-warp LLR scratch rows (32 values each)
-    uint32_t* gs;                // per-warp partial-sum scratch rows (32 words each)
-    unsigned long long gx_stride;// values per warp
-    unsigned long long gs_stride;// words per warp
-    int B, n, K, crc, L;
-    int W;                       // lanes per codeword (power of two >= L)
-    int lamS;                    // first LLR layer kept in shared memory (1..n)
-    int smem_x_rows;             // rows of 32 floats per warp
-    int smem_s_rows;             // rows of 32 words per warp
-    int s_off[kMaxN + 2];        // word-row offset of S layer lam (global for lam < lamS, shared otherwise)
-};
-
-__device__ __forceinline__ float ex2_approx(float x) {
-    float y;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float lg2_approx(float x) {
-    float y;
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
-// log(1 + exp(-x)) for x >= 0, in (0, ln 2].
-__device__ __forceinline__ float log1p_exp_neg(float x) {
-    return kLn2 * lg2_approx(1.0f + ex2_approx(-kLog2e * x));
-}
-
-// The reference's check-node rule (PolarCode.cpp:438-446): box-plus when both magnitudes
-// are strictly below 40, sign * min otherwise (sgn(0) = 0, which min() already yields).
-// Box-plus is evaluated as sign*min + log1p(e^-|a+b|) - log1p(e^-|a-b|): algebraically the
-// reference's log((e^(a+b)+1)/(e^a+e^b)), but with an absolute error of a few 1e-7 at every
-// magnitude (the literal form loses that much *relative* to e^40 in fp32).
-__device__ __forceinline__ float f_rule(float a, float b) {
-    const float ma = fabsf(a), mb = fabsf(b);
-    const float mn = fminf(ma, mb);
-    const float r = __int_as_float(__float_as_int(mn) | ((__float_as_int(a) ^ __float_as_int(b)) & 0x80000000));
-    const float s = fabsf(a + b), d = fabsf(a - b);
-    // branch-free: the correction is always evaluated (4 MUFU) and scaled by 0 above the threshold
-    const float diff = lg2_approx(1.0f + ex2_approx(-kLog2e * s)) - lg2_approx(1.0f + ex2_approx(-kLog2e * d));
-    const float scale = (fmaxf(ma, mb) < 40.0f) ? kLn2 : 0.0f;
-    return fmaf(diff, scale, r);
-}
-
-// log(1 + exp(x)) with the double-precision reference's corner behaviour
-// (PolarCode.cpp:483,505-506): +inf once exp(x) overflows a double (x > 709.78...),
-// exactly 0 once 1 + exp(x) rounds to 1 in double (x < -36.7368...).
-__device__ __forceinline__ float softplus_ref(float x) {
-    float r = fmaxf(x, 0.0f) + log1p_exp_neg(fabsf(x));
-    if (x >= 709.78271484375f) r = CUDART_INF_F;
-    if (x <= -36.7368f) r = 0.0f;
-    return r;
-}
-
-
-// ---- arithmetic by evaluation type. float: the throughput contract above. double: the reference's
-// literal formulas (PolarCode.cpp:438-446, 483, 505-506) evaluated in double like the reference itself.
-template <class Real> struct Arith;
-template <> struct Arith<float> {
-    static __device__ __forceinline__ float f(float a, float b) { return f_rule(a, b); }
-    static __device__ __forceinline__ float softplus(float x) { return softplus_ref(x); }
-    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
-};
-template <> struct Arith<double> {
-    static __device__ __forceinline__ double f(double a, double b) {
-        const double ma = fabs(a), mb = fabs(b);
-        if (40.0 > fmax(ma, mb)) return log((exp(a + b) + 1.0) / (exp(a) + exp(b)));
-        const double sa = (a < 0) ? -1.0 : (double)(a > 0), sb = (b < 0) ? -1.0 : (double)(b > 0);
-        return sa * sb * fmin(ma, mb);
-    }
-    static __device__ __forceinline__ double softplus(double x) { return log(1.0 + exp(x)); }
-    static __device__ __forceinline__ double inf() { return CUDART_INF; }
-};
-template <class Real> __device__ __forceinline__ Real rmin(Real a, Real b) { return a < b ? a : b; }
-template <class Real> __device__ __forceinline__ Real rmax(Real a, Real b) { return a > b ? a : b; }
-
-template <class Real>
-__device__ __forceinline__ Real group_min(Real v, int W) {
-    for (int o = W >> 1; o > 0; o >>= 1) v = rmin<Real>(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
-}
-template <class Real>
-__device__ __forceinline__ Real group_max(Real v, int W) {
-    for (int o = W >> 1; o > 0; o >>= 1) v = rmax<Real>(v, __shfl_xor_sync(FULL_MASK, v, o));
-    return v;
-}
-
-__device__ __forceinline__ unsigned long long set_ptr(unsigned long long p, int idx, unsigned lane) {
-    const int sh = 5 * idx;
-    return (p & ~(31ull << sh)) | ((unsigned long long)lane << sh);
-}
-__device__ __forceinline__ int get_ptr(unsigned long long p, int idx) { return (int)((p >> (5 * idx)) & 31ull); }
-
-}  // namespace
-
-#include "scl_fast.cuh"
+#include "polar_dev.cuh"
+#include "fast_variants.cuh"
 #include "scl_wide.cuh"
 
 namespace {
@@ -697,106 +587,20 @@ int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p, int elem = 4) {
     return 0;
 }
 
-// ---- fast-kernel variants (scl_fast.cuh) ----
-struct FastVariant {
-    int nlog, T, lamS, wlog, wpb, bps;
-    size_t gx_floats, gs_words;
-    int smem_per_warp;
-    cudaError_t (*launch)(const fast::Args&, int blocks, cudaStream_t st, const cudaLaunchAttribute* attrs, int nattrs);
-    cudaError_t (*prepare)();
+// The variant table lives in fast_parts.cu (four translation units, fast_variants.cuh); concatenated here in order.
+struct VariantTable {
+    std::vector<FastVariant> v;
+    VariantTable() {
+        v.insert(v.end(), kFastPart0, kFastPart0 + kFastPartN0);
+        v.insert(v.end(), kFastPart1, kFastPart1 + kFastPartN1);
+        v.insert(v.end(), kFastPart2, kFastPart2 + kFastPartN2);
+        v.insert(v.end(), kFastPart3, kFastPart3 + kFastPartN3);
+    }
 };
+const VariantTable& variant_table() { static VariantTable t; return t; }
+#define kFastVariants (variant_table().v.data())
+#define kNumFastVariants ((int)variant_table().v.size())
 
-template <class C, int WPB, int BPS>
-cudaError_t launch_fast(const fast::Args& a, int blocks, cudaStream_t st, const cudaLaunchAttribute* attrs, int nattrs) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(blocks); cfg.blockDim = dim3(WPB * 32);
-    cfg.dynamicSmemBytes = C::SMEM_PER_WARP * WPB; cfg.stream = st;
-    cfg.attrs = const_cast<cudaLaunchAttribute*>(attrs); cfg.numAttrs = nattrs;
-    return cudaLaunchKernelEx(&cfg, fast::scl_fast_kernel<C, WPB, BPS>, a);
-}
-template <class C, int WPB, int BPS>
-cudaError_t prepare_fast() {
-    return cudaFuncSetAttribute(fast::scl_fast_kernel<C, WPB, BPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                C::SMEM_PER_WARP * WPB);
-}
-#define POLAR_FAST(NLOG, T, LAMS, WLOG, WPB, BPS)                                                                   \
-    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG>::GS_WORDS, \
-      fast::Cfg<NLOG, T, LAMS, WLOG>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS>,               \
-      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG>, WPB, BPS> }
-
-#define POLAR_FAST_SG(NLOG, T, LAMS, WLOG, SG, WPB, BPS)                                                              \
-    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG, SG>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG, SG>::GS_WORDS, \
-      fast::Cfg<NLOG, T, LAMS, WLOG, SG>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG>, WPB, BPS>,               \
-      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG>, WPB, BPS> }
-
-#define POLAR_FAST_TM(NLOG, T, LAMS, WLOG, WPB, BPS)                                                                \
-    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::GS_WORDS, \
-      fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS>,               \
-      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS> }
-
-// (log2 N, virtual top layers, first shared-memory layer, log2 lanes per codeword, warps/block, blocks/SM).
-// pick_fast_variant() takes the first entry matching (n, lanes); POLAR_B200_FAST_VARIANT=<index> overrides.
-const FastVariant kFastVariants[] = {
-    // N=2048: layer 3 in the HBM/L2 scratch, layer 4 in tensor memory, layers 5-6 shared, 7-11 registers; 16 warps/SM
-    POLAR_FAST_TM(11, 3, 5, 5, 4, 4),  // 0: lists 17..32
-    POLAR_FAST_TM(11, 3, 5, 4, 4, 4),  // 1: lists 9..16 (2 codewords per warp)
-    POLAR_FAST_TM(11, 3, 5, 3, 4, 4),  // 2: lists 5..8  (4 codewords per warp)
-    POLAR_FAST_TM(11, 3, 5, 2, 4, 4),  // 3: lists 3..4  (8 codewords per warp)
-    POLAR_FAST_TM(11, 3, 5, 1, 4, 4),  // list 2 (16 codewords per warp)
-    POLAR_FAST_TM(11, 3, 5, 0, 4, 4),  // list 1 = plain SC (32 codewords per warp, lane = codeword)
-    // N=512: nothing per path leaves the SM: layer 3 in tensor memory, layer 4 shared, 5-9 registers; 20 warps/SM
-    POLAR_FAST_TM(9, 3, 4, 5, 4, 5),   // 4: lists 17..32
-    POLAR_FAST_TM(9, 3, 4, 4, 4, 5),   // 5: lists 9..16
-    POLAR_FAST_TM(9, 3, 4, 3, 4, 5),   // 6: lists 5..8
-    POLAR_FAST_TM(9, 3, 4, 2, 4, 5),   // 7: lists 3..4
-    POLAR_FAST_TM(9, 3, 4, 1, 4, 5),   // list 2
-    POLAR_FAST_TM(9, 3, 4, 0, 4, 5),   // list 1
-    // other block lengths, lists 17..32
-    POLAR_FAST_TM(10, 3, 5, 5, 4, 4),  // 8: N=1024: layer 3 scratch, layer 4 tensor memory, layer 5 shared
-    POLAR_FAST_TM(12, 3, 6, 5, 4, 4),  // 9: N=4096: layers 3-4 scratch, layer 5 tensor memory, layers 6-7 shared
-    POLAR_FAST(8, 3, 3, 5, 4, 4),      // 10: N=256
-    // alternates without tensor memory (POLAR_B200_FAST_VARIANT=<index>)
-    POLAR_FAST(11, 3, 5, 5, 4, 4),     // 11: N=2048 lists 17..32, layers 3-4 in the scratch
-    POLAR_FAST(11, 3, 6, 5, 4, 5),     // 12: N=2048 lists 17..32, layers 3-5 in the scratch, 20 warps/SM
-    POLAR_FAST(9, 3, 4, 5, 4, 5),      // 13: N=512 lists 17..32, layer 3 in the scratch
-    // one block per SM; the warps of a sub-partition start every codeword together (shared L0 instruction cache).
-    // Same placement as entries 0-5 / 6-11. Preferred by pick_fast_variant() unless POLAR_B200_SYNC=0.
-    POLAR_FAST_TM(11, 3, 5, 5, 16, 1), // 18: N=2048 lists 17..32
-    POLAR_FAST_TM(11, 3, 5, 4, 16, 1),
-    POLAR_FAST_TM(11, 3, 5, 3, 16, 1),
-    POLAR_FAST_TM(11, 3, 5, 2, 16, 1),
-    POLAR_FAST_TM(11, 3, 5, 1, 16, 1),
-    POLAR_FAST_TM(11, 3, 5, 0, 16, 1),
-    POLAR_FAST_TM(9, 3, 4, 5, 20, 1),  // 24: N=512 lists 17..32
-    POLAR_FAST_TM(9, 3, 4, 4, 20, 1),
-    POLAR_FAST_TM(9, 3, 4, 3, 20, 1),
-    POLAR_FAST_TM(9, 3, 4, 2, 20, 1),
-    POLAR_FAST_TM(9, 3, 4, 1, 20, 1),
-    POLAR_FAST_TM(9, 3, 4, 0, 20, 1),
-    POLAR_FAST_TM(10, 3, 5, 5, 16, 1), // 30: N=1024 lists 17..32
-    POLAR_FAST_TM(12, 3, 6, 5, 16, 1), // 31: N=4096 lists 17..32
-    POLAR_FAST(8, 3, 3, 5, 16, 1),     // 32: N=256 lists 17..32
-    // alternates (POLAR_B200_FAST_VARIANT=<index>)
-    POLAR_FAST(11, 3, 6, 5, 20, 1),    // 33: N=2048 lists 17..32 without tensor memory, 20 warps/SM
-    // other block lengths, lists 1..16 (2..32 codewords per warp), same placement as their list-32 entries
-    POLAR_FAST_TM(10, 3, 5, 4, 4, 4),  // 34: N=1024 lists 9..16
-    POLAR_FAST_TM(10, 3, 5, 3, 4, 4),
-    POLAR_FAST_TM(10, 3, 5, 2, 4, 4),
-    POLAR_FAST_TM(10, 3, 5, 1, 4, 4),
-    POLAR_FAST_TM(10, 3, 5, 0, 4, 4),
-    POLAR_FAST_TM(12, 3, 6, 4, 4, 4),  // 39: N=4096 lists 9..16
-    POLAR_FAST_TM(12, 3, 6, 3, 4, 4),
-    POLAR_FAST_TM(12, 3, 6, 2, 4, 4),
-    POLAR_FAST_TM(12, 3, 6, 1, 4, 4),
-    POLAR_FAST_TM(12, 3, 6, 0, 4, 4),
-    POLAR_FAST(8, 3, 3, 4, 4, 4),      // 44: N=256 lists 9..16
-    POLAR_FAST(8, 3, 3, 3, 4, 4),
-    POLAR_FAST(8, 3, 3, 2, 4, 4),
-    POLAR_FAST(8, 3, 3, 1, 4, 4),
-    POLAR_FAST(8, 3, 3, 0, 4, 4),
-};
-constexpr int kNumFastVariants = sizeof(kFastVariants) / sizeof(kFastVariants[0]);
 
 int pick_fast_variant(const polar_b200_ctx* c, int L, int B) {
     const int n = c->n;
