@@ -19,7 +19,7 @@ INC = os.path.join(ROOT, "include")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-I" + INC, "-I" + CSRC,
+    "-Xcompiler", "-fPIC", "-Xfatbin", "-compress-all", "-I" + INC, "-I" + CSRC,
 ]
 FAST_PARTS = 4          # fast_parts.cu is compiled once per quarter of the variant table (fast_variants.cuh)
 
