@@ -64,7 +64,8 @@ int polar_b200_info_words(int K);
  * (Bhattacharyya recursion, std::sort, rand() parity matrix) stays on the host
  * C++ side and is passed in as data, so this library is independent of
  * rand()/std::sort quirks:
- *   n            log2 of the block length N, 1 <= n <= 13
+ *   n            log2 of the block length N, 1 <= n <= 15 (the reference's block length is a uint16_t,
+ *                PolarCode.h:40); n <= 13 runs on the warp kernels, n = 14, 15 on the block-per-codeword kernel
  *   K            info bits; crc_bits parity ("CRC") bits, K + crc_bits <= N
  *   frozen_mask  [N] bytes, 1 = frozen, index = decoding position phi (_frozen_bits)
  *   info_order   [K + crc_bits] = prefix of _channel_order_descending: position of info
@@ -155,7 +156,7 @@ int polar_b200_count_errors(polar_b200_ctx* ctx, const uint32_t* info_packed,
  * get_bler_quick keeps doing that on the host.
  *   ebno_db   host, [n_ebno] (n_ebno <= 64); codeword i uses ebno_db[i % n_ebno]
  *   llr       device, [B][N] fp32 out;  truth_packed  device, [B][ceil(K/32)] out (the info bits)
- * K <= 2048 and N <= 8192.
+ * K <= 2048 and N <= 8192 (POLAR_B200_E_UNSUPPORTED beyond).
  */
 int polar_b200_synthesize(polar_b200_ctx* ctx, unsigned long long seed, long long first_index, int B,
                           const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed,

@@ -604,7 +604,7 @@ const VariantTable& variant_table() { static VariantTable t; return t; }
 
 int pick_fast_variant(const polar_b200_ctx* c, int L, int B) {
     const int n = c->n;
-    if (env_int("POLAR_B200_FORCE_GENERIC", 0) || env_int("POLAR_B200_FORCE_WIDE", 0)) return -1;
+    if (env_int("POLAR_B200_FORCE_GENERIC", 0) || env_int("POLAR_B200_FORCE_WIDE", 0) || n > kMaxNWarp) return -1;
     int wlog = 0;
     while ((1 << wlog) < L) ++wlog;                 // lanes per codeword
     if (L < 1 || wlog > 5) return -1;
@@ -689,12 +689,21 @@ int decode_wide_w(polar_b200_ctx* c, const typename Dom::Real* in0, const typena
     a.smem_s_rows = off;
     const size_t gx_rows = (size_t)(1 << n) - ((size_t)1 << (n - lamS + 1));
     const int smem = a.smem_x_rows * W * elem + a.smem_s_rows * W * 4 + fixed;
-    int blocks = c->sm_count * blocks_per_sm;
-    if (blocks > B) blocks = B;
     a.gx_stride = (gx_rows ? gx_rows : 1) * W;
     a.gs_stride = (gs_rows ? gs_rows : 1) * W;
-    const size_t need_gx = a.gx_stride * (size_t)(c->sm_count * blocks_per_sm) * elem;
-    const size_t need_gs = a.gs_stride * (size_t)(c->sm_count * blocks_per_sm) * sizeof(uint32_t);
+    // persistent blocks; at the largest block lengths the per-block scratch (all layers below lamS) is tens of MB,
+    // so the grid is also capped by a scratch budget (POLAR_B200_WIDE_SCRATCH_GB, default 16 GB of the 180 GB)
+    int max_blocks = c->sm_count * blocks_per_sm;
+    {
+        const double per_block = (double)a.gx_stride * elem + (double)a.gs_stride * sizeof(uint32_t);
+        const double budget = (double)env_int("POLAR_B200_WIDE_SCRATCH_GB", 16) * 1073741824.0;
+        const int fit = (int)(budget / per_block);
+        if (max_blocks > fit) max_blocks = fit < 1 ? 1 : fit;
+    }
+    int blocks = max_blocks;
+    if (blocks > B) blocks = B;
+    const size_t need_gx = a.gx_stride * (size_t)max_blocks * elem;
+    const size_t need_gs = a.gs_stride * (size_t)max_blocks * sizeof(uint32_t);
     if (need_gx > c->wgx_bytes) {
         if (c->d_wgx) cudaFree(c->d_wgx);
         c->d_wgx = nullptr; c->wgx_bytes = 0;
@@ -737,7 +746,7 @@ int decode_prob(polar_b200_ctx* c, const double* p0, const double* p1, int B, in
 // any list size: lists <= 32 on one warp, 33..127 on one block per codeword
 template <class Real>
 int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
-    if (L > 32 || env_int("POLAR_B200_FORCE_WIDE", 0)) return decode_wide<Real>(c, llr, B, L, info_packed, st);
+    if (L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0)) return decode_wide<Real>(c, llr, B, L, info_packed, st);
     return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
@@ -823,7 +832,7 @@ const char* polar_b200_strerror(int code) {
     switch (code) {
         case POLAR_B200_OK: return "ok";
         case POLAR_B200_E_ARG: return "polar_b200: invalid argument";
-        case POLAR_B200_E_UNSUPPORTED: return "polar_b200: parameter outside what this build supports (n <= 13, list <= 127)";
+        case POLAR_B200_E_UNSUPPORTED: return "polar_b200: parameter outside what this build supports (n <= 15, list <= 127)";
         case POLAR_B200_E_NOGPU: return "polar_b200: no usable CUDA device (there is no CPU fallback)";
         case POLAR_B200_E_BATCH: return "polar_b200: batch larger than the ctx's max_batch";
         case POLAR_B200_E_LIST: return "polar_b200: list size must be in 1..min(max_list, 127)";
@@ -965,8 +974,8 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
         if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || ch <= 0 || ch > B) ch = B;
         return ch;
     };
-    if (L > 32 || env_int("POLAR_B200_FORCE_WIDE", 0)) {
-        // wide lists: one block per codeword, a single chunk on the run stream
+    if (L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0)) {
+        // wide lists / N > 8192: one block per codeword, a single chunk on the run stream
         CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, c->st_run));
         int rc = decode_wide<float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
         if (rc) return rc;

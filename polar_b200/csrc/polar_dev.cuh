@@ -12,7 +12,9 @@
 namespace {
 
 constexpr int kMaxList = 127;       // the reference's own limit (uint8_t loop counters, PolarCode.cpp:497-605)
-constexpr int kMaxN = 13;          // log2 block length supported by the pointer packing (12 x 5 bits)
+constexpr int kMaxNWarp = 13;      // log2 block length of the warp kernels' pointer packing (12 layers x 5 bits)
+constexpr int kMaxN = 15;          // the reference's own limit: block length is a uint16_t (PolarCode.h:40); n = 14, 15
+                                   // run on the block-per-codeword kernel (8-bit pointers, 16 layers)
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 

@@ -117,6 +117,23 @@ WIDE = [
 ]
 
 
+@pytest.mark.parametrize("n,K,crc,L,B,eb", [(14, 8192, 16, 4, 6, 2.0), (14, 8192, 0, 1, 9, 2.5), (15, 16384, 16, 2, 4, 2.0),
+                                            (15, 16384, 0, 40, 2, 2.0)])
+def test_gpu_block_lengths_16384_and_32768(torch_cuda, n, K, crc, L, B, eb):
+    """n = 14, 15 (the reference's block length is a uint16_t, PolarCode.h:40): beyond the warp kernels' pointer
+    packing, so every list size runs on the block-per-codeword kernel; also in double."""
+    from polar_b200 import PolarCode
+    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+    assert all(np.array_equal(pc.construction()[k], port.construction()[k]) for k in ("frozen", "order", "crc_matrix"))
+    info, llr = awgn_llrs(port, B, eb, seed=70 + n + L)
+    want = port.decode_batch(llr, L, nthreads=os.cpu_count() or 1)
+    got = pc.decode_batch(llr, L)
+    assert pc.info(6) == -2
+    assert np.array_equal(got, want)
+    if L <= 4:
+        assert np.array_equal(pc.decode_batch_f64(llr[:2].astype(np.float64), L), want[:2])
+
+
 @pytest.mark.parametrize("n,K,crc,L,B,eb", WIDE)
 def test_gpu_wide_lists_match_oracle(torch_cuda, n, K, crc, L, B, eb):
     from polar_b200 import PolarCode

@@ -42,7 +42,7 @@ def test_abi_argument_validation_needs_no_gpu(native_libs):
     order = (C.c_uint16 * 4)(7, 6, 5, 3)
     assert lib.polar_b200_create(None, 0, 3, 4, 0, frozen, order, None, 1, 1) == -1
     assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 0, None, order, None, 1, 1) == -1
-    assert lib.polar_b200_create(C.byref(ctx), 0, 14, 4, 0, frozen, order, None, 1, 1) == -2   # n too large
+    assert lib.polar_b200_create(C.byref(ctx), 0, 16, 4, 0, frozen, order, None, 1, 1) == -2   # n too large (the reference stops at 15)
     assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 0, frozen, order, None, 128, 1) == -2  # list too large (the reference's own limit is 127)
     assert lib.polar_b200_create(C.byref(ctx), 0, 3, 4, 2, frozen, order, None, 1, 1) == -1    # crc without matrix
     assert lib.polar_b200_decode_scl_llr(None, None, 1, 1, None, None) == -1
