@@ -1,5 +1,6 @@
-// scl_fast.cuh -- the throughput kernel: list sizes 17..32 (and smaller lists run on 32 lanes),
-// block lengths 2^8..2^12, one codeword per warp, lane = list path.
+// scl_fast.cuh -- the throughput kernel: block lengths 2^8..2^12, list sizes 17..32 with one codeword per warp
+// (lane = list path) and list sizes 1..16 with 2..32 codewords per warp (W = list size rounded up to a power of
+// two lanes per codeword; list 1 = plain SC with lane = codeword).
 //
 // Same algorithm and the same arithmetic contract as the generic kernel in polar_b200.cu (the
 // reference's decode_scl_llr, PolarC/PolarCode.cpp:130-190, 422-644). What differs is purely where
@@ -22,7 +23,12 @@
 //   * the 2L -> L prune is "promote the best unlikely fork, demote the worst likely fork, until
 //     the best unlikely fork no longer beats the worst likely one", two warp REDUX per round;
 //     its first round is the common no-fork-survives exit. It yields exactly the reference's
-//     sort / threshold / index-order selection (PolarCode.cpp:528-553).
+//     sort / threshold / index-order selection (PolarCode.cpp:528-553);
+//   * with 16 or 32 codewords per warp (lists 1..2) the channel LLRs and the XS arrays of the warp's codewords
+//     are staged transposed ([position/4][codeword][4], [index][codeword]) so that the lanes of a warp read
+//     neighbouring words (top_solo_transposed);
+//   * compiled configurations are listed in fast_parts.cu (see fast_variants.cuh); DESIGN.md section 3 has the
+//     placement of every layer and section 5 the measurements behind each choice.
 #pragma once
 #include <type_traits>
 
