@@ -58,6 +58,17 @@ def recorded_traffic(cfg, batch):
         return None, None
 
 
+def issue_roofline(src, cw_per_s_per_gpu, sm_count, clocks):
+    try:
+        ipc = float(src["warp_instructions_per_codeword"])
+        mhz = float(clocks.get("sm_mhz") or clocks.get("sm_max_mhz"))
+        peak = sm_count * 4 * mhz * 1e6
+        return {"bound": "issue", "achieved": cw_per_s_per_gpu * ipc, "peak": peak, "unit": "warp-instr/s",
+                "frac": cw_per_s_per_gpu * ipc / peak, "warp_instr_per_codeword": ipc, "source": src.get("source")}
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -267,6 +278,7 @@ def run_ours(args):
         bytes_cw = 4 * N + (K + 7) // 8
         peak, peak_src = measured_peak()
         traffic, traffic_src = recorded_traffic(args.config, B)
+        sm_count = code.info(1)
         achieved = B * bytes_cw / (ms_step * 1e-3) / 1e9     # per GPU: one launch decodes this rank's B codewords
         out = {
             "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
@@ -285,6 +297,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok,
                     "pipelined_chunks": code.info(7)},
             "gpu_launches": int(launches),
+            # informational, beside the contract's HBM roofline: the decoder is bound by instruction issue, so the same
+            # rate is also stated against the issue-slot ceiling (148 SMs x 4 schedulers x SM clock), with the warp
+            # instructions per codeword taken from the committed ncu capture (profiles/ncu_traffic.json)
+            "issue_roofline": issue_roofline(traffic_src, value / world, sm_count, clocks),
             "clocks": clocks,
             "bler": float(counts[0, 0, 0] / counts[0, 0, 1]),
         }
