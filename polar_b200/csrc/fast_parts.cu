@@ -72,6 +72,10 @@ extern const FastVariant POLAR_CAT(kFastPart, POLAR_PART)[] = {
     POLAR_FAST(8, 3, 3, 2, 4, 4),
     POLAR_FAST(8, 3, 3, 1, 4, 4),
     POLAR_FAST(8, 3, 3, 0, 4, 4),
+    // alternates for plain SC at N=2048 (POLAR_B200_FAST_VARIANT=<index>; untested experiments for the next round):
+    // fewer virtual top layers = fewer recomputed check nodes, more layers in the per-warp scratch
+    POLAR_FAST_TM(11, 2, 5, 0, 4, 4),  // 49: layers 2-3 in the scratch
+    POLAR_FAST_TM(11, 1, 5, 0, 4, 4),  // 50: layers 1-3 in the scratch
 #endif
 };
 extern const int POLAR_CAT(kFastPartN, POLAR_PART) = (int)(sizeof(POLAR_CAT(kFastPart, POLAR_PART)) / sizeof(FastVariant));
