@@ -341,6 +341,39 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
             return;
         }
 #endif
+#if POLAR_TM_PIPE >= 2
+        if constexpr (SRC_TM) {
+            // EXPERIMENT (not the default, untested on hardware): tensor-memory source double-buffered over two explicit
+            // register sets. tcgen05.wait::ld waits for every earlier load, so the order is: load set 1, compute on
+            // set 0 (complete since the previous wait), wait, reload set 0, compute on set 1, wait.
+            static_assert(M % 8 == 0, "two groups of four per iteration");
+            float a0[4], b0[4], a1[4], b1[4];
+            tm_ld4(w.tm, a0); tm_ld4(w.tm + M, b0);
+            tm_wait_ld();
+#pragma unroll 1
+            for (int i0 = 0; i0 < M; i0 += 8) {
+                tm_ld4(w.tm + i0 + 4, a1); tm_ld4(w.tm + i0 + 4 + M, b1);
+                if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
+                float ca[4], cb[4], y[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { ca[j] = __shfl_sync(FULL_MASK, a0[j], pcol); cb[j] = __shfl_sync(FULL_MASK, b0[j], pcol); }
+                node4<ISG>(ca, cb, word, i0 & 31, y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[(i0 + j) * 32] = y[j];
+                tm_wait_ld();
+                const int nx = (i0 + 8 < M) ? i0 + 8 : i0;            // last iteration re-reads itself (harmless)
+                tm_ld4(w.tm + nx, a0); tm_ld4(w.tm + nx + M, b0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { ca[j] = __shfl_sync(FULL_MASK, a1[j], pcol); cb[j] = __shfl_sync(FULL_MASK, b1[j], pcol); }
+                node4<ISG>(ca, cb, word, (i0 + 4) & 31, y);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dst[(i0 + 4 + j) * 32] = y[j];
+                tm_wait_ld();
+            }
+            s.px = set_ptr(s.px, LAM - C::T, w.lane);
+            return;
+        }
+#endif
 #pragma unroll 1
         for (int i0 = 0; i0 < M; i0 += 4) {
             if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
