@@ -1045,6 +1045,15 @@ __device__ __forceinline__ void update_partial_sums(const Warp& w, Lane& s, int 
         return;
     }
 #endif
+#if POLAR_PS_SHORTCUT >= 2
+    if ((phi & 7) == 3) {
+        // EXPERIMENT (not the default, untested on hardware): a quarter of the odd leaves close a group of four
+        const uint32_t P2 = ((s.sreg ^ u) & 1u) | (u << 1);
+        const uint32_t P4 = (((s.sreg >> 1) ^ P2) & 3u) | (P2 << 2);
+        s.sreg = (s.sreg & ~0x78u) | (P4 << 3);
+        return;
+    }
+#endif
     const int t = __ffs(~phi) - 1;               // trailing ones, 1..NLOG
     uint32_t P = u;
     const int kmax = t < 5 ? t : 5;
