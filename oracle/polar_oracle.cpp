@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE ONLY -- not part of the product path.
 //
 // CPU restatement ("port" oracle) of the reference's LLR-domain SC / SCL polar
-// decoder, code construction, encoder and AWGN BLER harness
+// decoder, probability-domain decoder (decode_scl_p1), code construction, encoder and AWGN BLER harness
 // (reference: /root/reference/PolarC/PolarCode.{h,cpp}, cited per function below).
 //
 // It is written from the algorithm, not from the reference's data structures: the
@@ -14,8 +14,9 @@
 //
 // Parity pin: the reference ships no golden vectors or tests, so
 // this file is pinned against the UNMODIFIED reference compiled here into
-// oracle/_ref/libpolar_ref.so (tests/test_oracle_vs_ref.py) and against the
-// fixtures that binary generated (tests/golden/, made by tests/golden/make_golden.py).
+// oracle/_ref/libpolar_ref.so (tests/test_oracle.py::test_port_equals_compiled_reference,
+// ::test_port_probability_domain_equals_compiled_reference) and against the fixtures that
+// binary generated (tests/golden/, made by tests/golden/make_golden*.py).
 //
 // Language note: C++ rather than plain C because the reference's reliability order
 // is whatever libstdc++'s unstable std::sort makes of exact ties
