@@ -243,6 +243,9 @@ __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
 #ifndef POLAR_UNROLL2
 #define POLAR_UNROLL2 2
 #endif
+#ifndef POLAR_TOP_PIPE
+#define POLAR_TOP_PIPE 1
+#endif
 #ifndef POLAR_PS_SHORTCUT
 #define POLAR_PS_SHORTCUT 1
 #endif
@@ -585,6 +588,10 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
 #if POLAR_SW_PIPE
         load_sw(0, sw);
 #endif
+#if POLAR_TOP_PIPE >= 2
+        float va[2][CNT];
+        top_load_pair<C, NODE, 0>(w, 0, va);
+#endif
 #pragma unroll 1
         for (int wd = 0; wd < MT / 32; ++wd) {
 #if POLAR_SW_PIPE
@@ -614,6 +621,19 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                 if constexpr (DST_TM) { tm_st1(w.tm + beta, v[0][0]); tm_st1(w.tm + beta + 1, v[1][0]); }
                 else { dst[beta * 32] = v[0][0]; dst[(beta + 1) * 32] = v[1][0]; }
             };
+#if POLAR_TOP_PIPE >= 2
+            // EXPERIMENT (not the default, untested on hardware): the one-pair-ahead prefetch also runs across the
+            // 32-beta groups, so only the very first pair of a node is waited for (va is declared outside the loop)
+            float vb[2][CNT];
+#pragma unroll 1
+            for (int bi = 0; bi < 32; bi += 4) {
+                top_load_pair<C, NODE, 1>(w, wd * 32 + bi, vb);
+                compute_pair(bi, va);
+                const int nq = wd * 32 + bi + 4;
+                top_load_pair<C, NODE, 0>(w, nq < MT ? nq : MT - 4, va);         // the last one re-reads (harmless)
+                compute_pair(bi + 2, vb);
+            }
+#else
             float va[2][CNT], vb[2][CNT];
             top_load_pair<C, NODE, 0>(w, wd * 32, va);
 #pragma unroll 1
@@ -623,6 +643,7 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                 top_load_pair<C, NODE, 0>(w, wd * 32 + ((bi + 4) & 31), va);   // wraps harmlessly
                 compute_pair(bi + 2, vb);
             }
+#endif
 #if POLAR_SW_PIPE
             static_for<0, (1 << T)>([&](auto i_c) { sw[decltype(i_c)::value] = swn[decltype(i_c)::value]; });
 #endif
