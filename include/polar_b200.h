@@ -47,7 +47,21 @@ enum {
 };
 
 /* ABI version of this header; polar_b200_abi_version() must return the same value. */
-#define POLAR_B200_ABI_VERSION 1
+#define POLAR_B200_ABI_VERSION 2
+
+/*
+ * Arithmetic modes of the LLR-domain decoder.
+ *   FP32    the throughput kernels alone: float LLRs, the reference's rules of order, hardware exp2/log2. Decisions
+ *           taken on a margin smaller than float rounding can differ from the double reference (measured: 1-2.5 in
+ *           10^4 codewords at 1 dB, none at >= 1.5 dB).
+ *   STRICT  FP32, plus: every kernel records the smallest margin (gap between the worst kept and the best dropped
+ *           fork metric; |LLR| for list 1; runner-up gap of the final pick) each codeword was decided with, and every
+ *           codeword whose margin is below tau (polar_b200_set_strict_tau) is decoded again in double. Block lengths /
+ *           lists without a margin-reporting kernel run entirely in double. This is what the drop-in class uses.
+ *   F64     everything in double with the reference's literal formulas (PolarCode.cpp:438-446, 483, 505-506).
+ */
+enum { POLAR_B200_MODE_FP32 = 0, POLAR_B200_MODE_STRICT = 1, POLAR_B200_MODE_F64 = 2 };
+#define POLAR_B200_DEFAULT_STRICT_TAU 1.0e-4f
 int polar_b200_abi_version(void);
 
 /* Human-readable text for any value returned by this library. */
@@ -97,14 +111,40 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* ctx, const float* llr, int B, int 
                               uint32_t* info_packed, void* cuda_stream);
 
 /*
+ * Same with an explicit arithmetic mode (polar_b200_decode_scl_llr is mode FP32).
+ *   margin   device, [B] floats out, or NULL: the smallest decision margin of every codeword (fast kernels only:
+ *            POLAR_B200_E_UNSUPPORTED where (n, L) has none). +inf = no close decision at all.
+ * llr should be 16-byte aligned; other addresses are decoded by the generic kernel (slower).
+ * One call per ctx is in flight at a time: a call on another stream first waits (on the device) for the previous
+ * call of this ctx, because all calls share the ctx's scratch buffers.
+ */
+int polar_b200_decode_scl_llr_ex(polar_b200_ctx* ctx, const float* llr, int B, int L, uint32_t* info_packed,
+                                 int mode, float* margin, void* cuda_stream);
+
+/* Margin threshold of STRICT mode (default POLAR_B200_DEFAULT_STRICT_TAU; env POLAR_B200_STRICT_TAU overrides). */
+int polar_b200_set_strict_tau(polar_b200_ctx* ctx, float tau);
+
+/* Grow the staging buffers of the *_host entry points to max_batch codewords (they also grow on demand). */
+int polar_b200_reserve(polar_b200_ctx* ctx, int max_batch);
+
+/*
  * Same, host memory in and out: H2D copy of llr, decode, D2H copy of the packed bits; the
  * result is valid on return. The batch is cut into a few chunks whose transfers and decodes
  * overlap on internal streams (pinned host memory makes the copies truly asynchronous);
  * `cuda_stream` is only synchronised on entry. This is the end-to-end path the host class and
- * bench.py's `e2e` leg use. B <= max_batch.
+ * bench.py's `e2e` leg use. Staging grows on demand (polar_b200_reserve).
  */
 int polar_b200_decode_scl_llr_host(polar_b200_ctx* ctx, const float* llr_host, int B, int L,
                                    uint32_t* info_packed_host, void* cuda_stream);
+int polar_b200_decode_scl_llr_host_ex(polar_b200_ctx* ctx, const float* llr_host, int B, int L,
+                                      uint32_t* info_packed_host, int mode, void* cuda_stream);
+/*
+ * STRICT mode on double LLRs (what PolarCode::get_bler_quick feeds the decoder, PolarCode.cpp:752-756): the fp32
+ * kernels decode the LLRs rounded to float, the flagged codewords are decoded again in double on the caller's
+ * doubles. Host memory, synchronous.
+ */
+int polar_b200_decode_scl_llr_f64_strict_host(polar_b200_ctx* ctx, const double* llr_host, int B, int L,
+                                              uint32_t* info_packed_host, void* cuda_stream);
 
 /*
  * Reference-precision mode: the same decoder evaluated in double with the reference's literal
@@ -173,7 +213,8 @@ enum {
     POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode,
                                             -2 = wide-list kernel (lists 33..127), -3 = wide-list kernel in f64,
                                             -4 = probability-domain decoder */
-    POLAR_B200_INFO_HOST_CHUNKS = 7      /* chunks the last *_host call was pipelined in            */
+    POLAR_B200_INFO_HOST_CHUNKS = 7,     /* chunks the last *_host call was pipelined in            */
+    POLAR_B200_INFO_LAST_FLAGGED = 8     /* codewords the last STRICT call decoded again in double (waits for it) */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
 

@@ -38,6 +38,11 @@ def dev():
         lib.polar_b200_destroy.argtypes = [vp]
         lib.polar_b200_decode_scl_llr.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_b200_decode_scl_llr_host.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_decode_scl_llr_ex.argtypes = [vp, vp, ip, ip, vp, ip, vp, vp]
+        lib.polar_b200_decode_scl_llr_host_ex.argtypes = [vp, vp, ip, ip, vp, ip, vp]
+        lib.polar_b200_decode_scl_llr_f64_strict_host.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_b200_set_strict_tau.argtypes = [vp, C.c_float]
+        lib.polar_b200_reserve.argtypes = [vp, ip]
         lib.polar_b200_count_errors.argtypes = [vp, vp, vp, ip, vp, vp, vp]
         lib.polar_b200_decode_scl_llr_f64.argtypes = [vp, vp, ip, ip, vp, vp]
         lib.polar_b200_decode_scl_llr_f64_host.argtypes = [vp, vp, ip, ip, vp, vp]
@@ -65,7 +70,10 @@ def host():
         lib.polar_host_encode.argtypes = [vp, vp, ip, vp]
         lib.polar_host_decode_scl_llr.argtypes = [vp, vp, ip, vp]
         lib.polar_host_decode_batch_packed.argtypes = [vp, vp, ip, ip, vp]
-        lib.polar_host_decode_device.argtypes = [vp, vp, ip, ip, vp, vp]
+        lib.polar_host_decode_device.argtypes = [vp, vp, ip, ip, vp, vp, vp]
+        lib.polar_host_set_mode.argtypes = [vp, ip]
+        lib.polar_host_get_mode.argtypes = [vp]
+        lib.polar_host_decode_batch_packed_double.argtypes = [vp, vp, ip, ip, vp]
         lib.polar_host_decode_batch_packed_f64.argtypes = [vp, vp, ip, ip, vp]
         lib.polar_host_decode_p1_batch_packed.argtypes = [vp, vp, vp, ip, ip, vp]
         lib.polar_host_decode_scl_p1.argtypes = [vp, vp, vp, ip, vp]

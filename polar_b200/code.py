@@ -36,8 +36,11 @@ def pack_bits(bits):
     return np.packbits(pad, axis=-1, bitorder="little").view(np.uint32).reshape(B, KW)
 
 
+MODES = {"fp32": 0, "strict": 1, "f64": 2}
+
+
 class PolarCode:
-    def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True, device=0):
+    def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True, device=0, mode=None):
         """n = log2(block length) as in the C++ reference (PolarCode.h:19). reseed=True calls
         srand(1) first so the random parity matrix (PolarCode.cpp:51-56) is the one a fresh
         reference process draws."""
@@ -49,6 +52,31 @@ class PolarCode:
         self._h = lib.polar_host_create(self.n, self.K, float(epsilon), self.crc, 1 if reseed else 0, self.device)
         if not self._h:
             raise _lib.PolarB200Error("PolarCode: " + lib.polar_host_last_error().decode())
+        if mode is not None:
+            self.mode = mode
+
+    # arithmetic mode of every decode (include/polar_b200.h): "fp32" kernels alone, "strict" (default: fp32 kernels +
+    # double re-decode of the codewords with a close decision), "f64" (everything in double)
+    @property
+    def mode(self):
+        m = _lib.host().polar_host_get_mode(self._h)
+        return [k for k, v in MODES.items() if v == m][0]
+
+    @mode.setter
+    def mode(self, m):
+        _lib.host().polar_host_set_mode(self._h, MODES[m] if isinstance(m, str) else int(m))
+
+    class _Mode:
+        def __init__(self, code, mode):
+            self.code, self.new = code, mode
+
+        def __enter__(self):
+            self.old = self.code.mode
+            if self.new is not None:
+                self.code.mode = self.new
+
+        def __exit__(self, *a):
+            self.code.mode = self.old
 
     def close(self):
         if self._h:
@@ -90,7 +118,7 @@ class PolarCode:
         return out
 
     # ---- batched, host memory (numpy or pinned torch CPU tensors) ----
-    def decode_batch(self, llr, list_size, packed=False, out=None):
+    def decode_batch(self, llr, list_size, packed=False, out=None, mode=None):
         """llr: [B][N] float32 in host memory. Returns [B][K] uint8 bits, or the packed
         [B][KW] uint32 words if packed=True. H2D, decode and D2H all happen inside the call."""
         if isinstance(llr, np.ndarray):
@@ -98,10 +126,21 @@ class PolarCode:
         B = int(llr.shape[0])
         if out is None:
             out = np.zeros((B, self.KW), np.uint32)
-        _lib.check_host(_lib.host().polar_host_decode_batch_packed(self._h, _ptr(llr), B, int(list_size), _ptr(out)))
+        with self._Mode(self, mode):
+            _lib.check_host(_lib.host().polar_host_decode_batch_packed(self._h, _ptr(llr), B, int(list_size), _ptr(out)))
         if packed or not isinstance(out, np.ndarray):
             return out
         return unpack_bits(out, self.K)
+
+    def decode_batch_double(self, llr, list_size, packed=False, mode=None):
+        """[B][N] float64 host LLRs in the current arithmetic mode; in "strict" the fp32 kernels decode the rounded
+        LLRs and the flagged codewords are decoded again in double on these doubles (what get_bler_quick does)."""
+        llr = np.ascontiguousarray(llr, np.float64).reshape(-1, self.N)
+        out = np.zeros((llr.shape[0], self.KW), np.uint32)
+        with self._Mode(self, mode):
+            _lib.check_host(_lib.host().polar_host_decode_batch_packed_double(self._h, llr.ctypes.data, llr.shape[0],
+                                                                              int(list_size), out.ctypes.data))
+        return out if packed else unpack_bits(out, self.K)
 
     def decode_batch_f64(self, llr, list_size, packed=False):
         """Reference-precision mode: [B][N] float64 host LLRs, evaluated in double on the GPU with the
@@ -136,7 +175,8 @@ class PolarCode:
         _lib.host().polar_host_set_exact(self._h, 1 if exact else 0)
 
     # ---- batched, device memory (torch CUDA tensors), asynchronous on the current stream ----
-    def decode_device(self, llr, list_size, out=None, stream=None):
+    def decode_device(self, llr, list_size, out=None, stream=None, mode=None, margin=None):
+        """margin: optional float32 cuda tensor [B], receives every codeword's smallest decision margin."""
         import torch
         assert llr.is_cuda and llr.dtype == torch.float32 and llr.is_contiguous()
         B = llr.numel() // self.N
@@ -144,9 +184,19 @@ class PolarCode:
             out = torch.empty((B, self.KW), dtype=torch.int32, device=llr.device)
         if stream is None:
             stream = torch.cuda.current_stream(llr.device).cuda_stream
-        _lib.check_host(_lib.host().polar_host_decode_device(self._h, llr.data_ptr(), B, int(list_size), out.data_ptr(),
-                                                             C.c_void_p(stream)))
+        with self._Mode(self, mode):
+            _lib.check_host(_lib.host().polar_host_decode_device(self._h, llr.data_ptr(), B, int(list_size), out.data_ptr(),
+                                                                 C.c_void_p(stream),
+                                                                 margin.data_ptr() if margin is not None else None))
         return out
+
+    @property
+    def last_flagged(self):
+        """codewords the last strict-mode call decoded again in double (synchronises)"""
+        return self.info(8)
+
+    def set_strict_tau(self, tau):
+        _lib.check(_lib.dev().polar_b200_set_strict_tau(self.ctx(1), float(tau)))
 
     def count_errors(self, dec, truth, block_err=None, n_err=None, stream=None):
         """device tensors [B][KW] int32; fills block_err (uint8 [B]) / adds to n_err (int64 [1])."""

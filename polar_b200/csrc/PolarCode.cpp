@@ -24,7 +24,13 @@ void check(int rc, const char* what) {
 PolarCode::PolarCode(uint8_t num_layers, uint16_t info_length, double epsilon, uint16_t crc_size)
     : _n(num_layers), _info_length(info_length), _crc_size(crc_size), _design_epsilon(epsilon) {
     const char* ex = getenv("POLAR_B200_EXACT");
-    exact_arithmetic = ex && *ex && *ex != '0';
+    if (ex && *ex && *ex != '0') arithmetic_mode = POLAR_B200_MODE_F64;
+    if (const char* m = getenv("POLAR_B200_MODE")) {
+        const std::string v(m);
+        if (v == "fp32") arithmetic_mode = POLAR_B200_MODE_FP32;
+        else if (v == "strict") arithmetic_mode = POLAR_B200_MODE_STRICT;
+        else if (v == "f64") arithmetic_mode = POLAR_B200_MODE_F64;
+    }
     _block_length = (uint16_t)(1 << _n);
     _frozen_bits.resize(_block_length);
     _bit_rev_order.resize(_block_length);
@@ -98,7 +104,11 @@ std::vector<uint8_t> PolarCode::encode(std::vector<uint8_t> info_bits) {
 
 polar_b200_ctx* PolarCode::device_ctx(int min_batch) {
     if (_ctx && _ctx_batch >= min_batch) return _ctx;
-    if (_ctx) { polar_b200_destroy(_ctx); _ctx = nullptr; }
+    if (_ctx) {     // the ctx (tables, scratch, counters, handles given out) stays; only its host staging grows
+        check(polar_b200_reserve(_ctx, min_batch), "polar_b200_reserve");
+        _ctx_batch = min_batch;
+        return _ctx;
+    }
     std::vector<uint8_t> flat((size_t)_crc_size * _info_length);
     for (int r = 0; r < _crc_size; ++r)
         std::copy(_crc_matrix[r].begin(), _crc_matrix[r].end(), flat.begin() + (size_t)r * _info_length);
@@ -113,8 +123,21 @@ polar_b200_ctx* PolarCode::device_ctx(int min_batch) {
 void PolarCode::decode_scl_llr_batch_packed(const float* llr, int B, uint16_t list_size, uint32_t* info_packed) {
     if (list_size >= 128)   // the reference's uint8_t loop counters never terminate here (PolarCode.cpp:525)
         throw std::invalid_argument("PolarCode: list_size must be < 128");
-    check(polar_b200_decode_scl_llr_host(device_ctx(B), llr, B, list_size, info_packed, nullptr),
-          "polar_b200_decode_scl_llr_host");
+    check(polar_b200_decode_scl_llr_host_ex(device_ctx(B), llr, B, list_size, info_packed, arithmetic_mode, nullptr),
+          "polar_b200_decode_scl_llr_host_ex");
+}
+
+void PolarCode::decode_scl_llr_batch_packed_double(const double* llr, int B, uint16_t list_size, uint32_t* info_packed) {
+    if (list_size >= 128) throw std::invalid_argument("PolarCode: list_size must be < 128");
+    if (arithmetic_mode == POLAR_B200_MODE_F64) return decode_scl_llr_batch_packed_f64(llr, B, list_size, info_packed);
+    if (arithmetic_mode == POLAR_B200_MODE_STRICT) {
+        check(polar_b200_decode_scl_llr_f64_strict_host(device_ctx(B), llr, B, list_size, info_packed, nullptr),
+              "polar_b200_decode_scl_llr_f64_strict_host");
+        return;
+    }
+    std::vector<float> f((size_t)B * _block_length);
+    for (size_t i = 0; i < f.size(); ++i) f[i] = (float)llr[i];
+    decode_scl_llr_batch_packed(f.data(), B, list_size, info_packed);
 }
 
 void PolarCode::decode_scl_llr_batch_packed_f64(const double* llr, int B, uint16_t list_size, uint32_t* info_packed) {
@@ -134,14 +157,16 @@ std::vector<uint8_t> PolarCode::decode_scl_llr_batch(const float* llr, int B, ui
 }
 
 void PolarCode::decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev,
-                                      void* cuda_stream) {
-    check(polar_b200_decode_scl_llr(device_ctx(1), llr_dev, B, list_size, info_packed_dev, cuda_stream),
-          "polar_b200_decode_scl_llr");
+                                      void* cuda_stream, float* margin_dev) {
+    check(polar_b200_decode_scl_llr_ex(device_ctx(1), llr_dev, B, list_size, info_packed_dev, arithmetic_mode, margin_dev,
+                                       cuda_stream),
+          "polar_b200_decode_scl_llr_ex");
 }
 
 // PolarCode.cpp:130-148: one codeword by value in, K bytes out.
 std::vector<uint8_t> PolarCode::decode_scl_llr(std::vector<double> llr, uint16_t list_size) {
-    if (exact_arithmetic) {
+    if (arithmetic_mode != POLAR_B200_MODE_FP32) {
+        // one codeword is latency-bound either way: straight to double, the reference's own arithmetic
         llr.at(_block_length - 1);
         std::vector<uint32_t> packed(info_words());
         decode_scl_llr_batch_packed_f64(llr.data(), 1, list_size, packed.data());
@@ -207,19 +232,16 @@ std::vector<std::vector<double>> PolarCode::get_bler_quick(std::vector<double> e
 
     // phase 2: ok[l][e][run]
     std::vector<uint8_t> ok(nl * ne * (size_t)max_runs, 0);
-    std::vector<float> llr(exact_arithmetic ? 0 : (size_t)max_runs * N);
-    std::vector<double> llr64(exact_arithmetic ? (size_t)max_runs * N : 0);
+    std::vector<double> llr64((size_t)max_runs * N);
     std::vector<uint32_t> dec((size_t)max_runs * KW);
     for (size_t ie = 0; ie < ne; ++ie) {
         const double a = std::pow(10.0f, ebno_vec[ie] / 20) * std::sqrt(((double)K) / ((double)N));
         for (size_t i = 0; i < noise.size(); ++i) {
             const double r = a * (double)bpsk[i] + std::sqrt(N_0 / 2) * noise[i];
-            const double v = -4 * r * a / N_0;
-            if (exact_arithmetic) llr64[i] = v; else llr[i] = (float)v;
+            llr64[i] = -4 * r * a / N_0;
         }
         for (size_t il = 0; il < nl; ++il) {
-            if (exact_arithmetic) decode_scl_llr_batch_packed_f64(llr64.data(), max_runs, list_size_vec[il], dec.data());
-            else decode_scl_llr_batch_packed(llr.data(), max_runs, list_size_vec[il], dec.data());
+            decode_scl_llr_batch_packed_double(llr64.data(), max_runs, list_size_vec[il], dec.data());
             for (int run = 0; run < max_runs; ++run) {
                 bool same = true;
                 for (int w = 0; w < KW; ++w) same &= dec[(size_t)run * KW + w] == truth[(size_t)run * KW + w];
@@ -315,9 +337,10 @@ int polar_host_decode_batch_packed(void* h, const float* llr, int B, int L, uint
     return guarded([&] { p->decode_scl_llr_batch_packed(llr, B, (uint16_t)L, info_packed); });
 }
 
-int polar_host_decode_device(void* h, const float* llr_dev, int B, int L, uint32_t* info_packed_dev, void* stream) {
+int polar_host_decode_device(void* h, const float* llr_dev, int B, int L, uint32_t* info_packed_dev, void* stream,
+                             float* margin_dev) {
     PolarCode* p = static_cast<PolarCode*>(h);
-    return guarded([&] { p->decode_scl_llr_device(llr_dev, B, (uint16_t)L, info_packed_dev, stream); });
+    return guarded([&] { p->decode_scl_llr_device(llr_dev, B, (uint16_t)L, info_packed_dev, stream, margin_dev); });
 }
 
 int polar_host_decode_batch_packed_f64(void* h, const double* llr, int B, int L, uint32_t* info_packed) {
@@ -340,7 +363,16 @@ int polar_host_decode_scl_p1(void* h, const double* p1, const double* p0, int L,
     });
 }
 
-void polar_host_set_exact(void* h, int exact) { static_cast<PolarCode*>(h)->exact_arithmetic = exact != 0; }
+void polar_host_set_exact(void* h, int exact) {
+    static_cast<PolarCode*>(h)->arithmetic_mode = exact ? POLAR_B200_MODE_F64 : POLAR_B200_MODE_STRICT;
+}
+void polar_host_set_mode(void* h, int mode) { static_cast<PolarCode*>(h)->arithmetic_mode = mode; }
+int polar_host_get_mode(void* h) { return static_cast<PolarCode*>(h)->arithmetic_mode; }
+
+int polar_host_decode_batch_packed_double(void* h, const double* llr, int B, int L, uint32_t* info_packed) {
+    PolarCode* p = static_cast<PolarCode*>(h);
+    return guarded([&] { p->decode_scl_llr_batch_packed_double(llr, B, (uint16_t)L, info_packed); });
+}
 
 void* polar_host_ctx(void* h, int min_batch) {
     PolarCode* p = static_cast<PolarCode*>(h);

@@ -33,7 +33,7 @@ public:
     // GPU in double (the reference's harness never calls it, PolarCode.cpp:755 is commented out).
     std::vector<uint8_t> decode_scl_p1(std::vector<double> p1, std::vector<double> p0, uint16_t list_size);
     // PolarCode.h:32 / PolarCode.cpp:130-190. One codeword, GPU, latency-bound; kept for source
-    // compatibility. LLRs are rounded to float before decoding.
+    // compatibility. Evaluated in double like the reference unless arithmetic_mode is FP32.
     std::vector<uint8_t> decode_scl_llr(std::vector<double> llr, uint16_t list_size);
     // PolarCode.h:34 / PolarCode.cpp:658-785. Same RNG objects in the same call order, same
     // counting rules (early stop, decoded-at-lower-Eb/N0 shortcut) replayed on the host over
@@ -49,8 +49,11 @@ public:
     void decode_scl_llr_batch_packed_f64(const double* llr, int B, uint16_t list_size, uint32_t* info_packed);
     // Probability domain, batched: p1, p0 host [B][N] doubles; packed output.
     void decode_scl_p1_batch_packed(const double* p1, const double* p0, int B, uint16_t list_size, uint32_t* info_packed);
-    // Device pointers, asynchronous on `cuda_stream` (a cudaStream_t).
-    void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream);
+    // double LLRs in arithmetic_mode (STRICT: float kernels + double re-decode of the flagged codewords on these doubles)
+    void decode_scl_llr_batch_packed_double(const double* llr, int B, uint16_t list_size, uint32_t* info_packed);
+    // Device pointers, asynchronous on `cuda_stream` (a cudaStream_t). margin_dev: optional [B] floats (decision margins).
+    void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream,
+                               float* margin_dev = nullptr);
 
     int block_length() const { return _block_length; }
     int info_length() const { return _info_length; }
@@ -68,9 +71,11 @@ public:
     int bler_max_runs = 1000;
     bool bler_verbose = true;      // the reference's "Running iteration ..." lines
     int device = 0;                // CUDA device ordinal
-    // true: decode_scl_llr / get_bler_quick evaluate in double (polar_b200_decode_scl_llr_f64*), an order of
-    // magnitude slower; default false, or true when the environment has POLAR_B200_EXACT=1
-    bool exact_arithmetic = false;
+    // Arithmetic of every decode (include/polar_b200.h, POLAR_B200_MODE_*): 0 = FP32 kernels alone, 1 = STRICT (default:
+    // FP32 kernels, codewords with a decision closer than tau decoded again in double -- reproduces the reference's
+    // decisions), 2 = F64 (everything in double, an order of magnitude slower). Environment: POLAR_B200_MODE=fp32|strict|f64
+    // (POLAR_B200_EXACT=1 is f64).
+    int arithmetic_mode = 1;
 
 private:
     uint8_t _n;

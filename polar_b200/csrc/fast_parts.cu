@@ -76,6 +76,12 @@ extern const FastVariant POLAR_CAT(kFastPart, POLAR_PART)[] = {
     // fewer virtual top layers = fewer recomputed check nodes, more layers in the per-warp scratch
     POLAR_FAST_TM(11, 2, 5, 0, 4, 4),  // 49: layers 2-3 in the scratch
     POLAR_FAST_TM(11, 1, 5, 0, 4, 4),  // 50: layers 1-3 in the scratch
+    // N=2048 with every per-path layer on the SM: layer 3 in tensor memory (256 columns per warp), layers 4-6 in shared
+    // memory (28 KB per warp), 8 warps/SM; only the one-word partial-sum layer stays in shared memory
+    POLAR_FAST_TM_SG(11, 3, 4, 5, 2, 8, 1),  // 51: lists 17..32
+    POLAR_FAST_TM_SG(11, 3, 4, 2, 2, 8, 1),  // 52: lists 3..4
+    POLAR_FAST_TM_SG(11, 3, 4, 0, 2, 8, 1),  // 53: list 1
+    POLAR_FAST_TM_SG(11, 3, 4, 1, 2, 8, 1),  // 54: list 2
 #endif
 };
 extern const int POLAR_CAT(kFastPartN, POLAR_PART) = (int)(sizeof(POLAR_CAT(kFastPart, POLAR_PART)) / sizeof(FastVariant));

@@ -50,4 +50,9 @@ cudaError_t prepare_fast() {
       fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS>,               \
       prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, 16, 1>, WPB, BPS> }
 
+#define POLAR_FAST_TM_SG(NLOG, T, LAMS, WLOG, SG, WPB, BPS)                                                            \
+    { NLOG, T, LAMS, WLOG, WPB, BPS, fast::Cfg<NLOG, T, LAMS, WLOG, SG, 1>::GX_FLOATS, fast::Cfg<NLOG, T, LAMS, WLOG, SG, 1>::GS_WORDS, \
+      fast::Cfg<NLOG, T, LAMS, WLOG, SG, 1>::SMEM_PER_WARP, launch_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG, 1>, WPB, BPS>,               \
+      prepare_fast<fast::Cfg<NLOG, T, LAMS, WLOG, SG, 1>, WPB, BPS> }
+
 }  // namespace

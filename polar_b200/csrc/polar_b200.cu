@@ -53,8 +53,8 @@ namespace {
 //   smem_x_rows rows of 32 floats (LLR layers lamS..n-1), smem_s_rows rows of 32 words
 //   (partial-sum layers >= max(lamS,1), except layer n which is a register), 32 bytes of scatter
 //   scratch.
-template <class Real>
-__global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real> a) {
+template <class Real, class In>
+__global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real, In> a) {
     constexpr int ROWB = 32 * (int)sizeof(Real);         // bytes of one [32 lanes] row
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31;
@@ -91,10 +91,13 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real>
         return gs + ((size_t)(a.s_off[lam] + w) << 5);
     };
 
-    for (int grp = gwarp; grp * G < a.B; grp += total_warps) {
-        const int cw = grp * G + (lane / W);
-        const bool valid = cw < a.B;
-        const Real* chan = a.llr + (size_t)(valid ? cw : a.B - 1) * N;
+    // list mode: decode only the codewords named by a.list[0 .. *a.count) (rows of llr / out are still indexed by codeword)
+    const int nB = a.list ? *a.count : a.B;
+    for (int grp = gwarp; grp * G < nB; grp += total_warps) {
+        const int idx = grp * G + (lane / W);
+        const bool valid = idx < nB;
+        const int row = valid ? idx : nB - 1;
+        const In* chan = a.llr + (size_t)(a.list ? a.list[row] : row) * N;
 
         // Per-path state. Reference bookkeeping reproduced: the free-path stack is filled
         // 0..L-1 (PolarCode.cpp:250-256) and the first path popped is L-1 (:259-263).
@@ -125,7 +128,7 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real>
                         if (lam == 1) {
                             // channel layer: reference pairs are (2k, 2k+1); k runs in memory
                             // order, the result lands at the bit-reversed position.
-                            x0 = chan[2 * i]; x1 = chan[2 * i + 1];
+                            x0 = (Real)chan[2 * i]; x1 = (Real)chan[2 * i + 1];
                             beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
                         } else {
                             x0 = src[(size_t)i << 5];
@@ -313,8 +316,8 @@ __global__ void __launch_bounds__(256) scl_decode_kernel(const DecodeArgsT<Real>
         for (int g = 0; g < G; ++g) {
             const int wl = __shfl_sync(FULL_MASK, gbase + win_slot, g * W);
             const bool wa = __shfl_sync(FULL_MASK, (int)win_active, g * W);
-            const int cwg = grp * G + g;
-            if (cwg >= a.B) break;
+            if (grp * G + g >= nB) break;
+            const int cwg = a.list ? a.list[grp * G + g] : grp * G + g;
             const uint32_t* U = srow(0, 0) + wl;
             for (int t = lane; t < KW; t += 32) {
                 uint32_t word = 0;
@@ -492,13 +495,11 @@ struct polar_b200_ctx {
     uint32_t* d_crc_rows = nullptr;        // synth: parity matrix rows packed over the info index
     float* d_amp = nullptr;                // synth: per-Eb/N0 amplitudes (up to 64)
     void* d_gx = nullptr;                  // generic-kernel LLR scratch (float or double rows)
-    int scratch_elem = 4;
     double* d_llr64_stage = nullptr;       // host entry point of the f64 mode
     double* d_prob_stage = nullptr;        // host entry point of the probability-domain decoder: p0 then p1
     uint32_t* d_gs = nullptr;
-    size_t gx_stride = 0, gs_stride = 0;   // per warp, elements
-    int scratch_warps = 0;
-    int scratch_lamS = -1;
+    size_t gx_stride = 0, gs_stride = 0;   // per warp, elements (of the last launch)
+    size_t gx_bytes = 0, gs_bytes = 0;     // capacity
     float* d_llr_stage = nullptr;
     uint32_t* d_out_stage = nullptr;
     // host entry point: H2D / decode / D2H of consecutive chunks overlap on three internal streams
@@ -515,6 +516,24 @@ struct polar_b200_ctx {
     size_t fgx_bytes = 0, fgs_bytes = 0;   // capacity of the two scratch buffers (shared by all variants, grown on demand)
     size_t l2_window = 0;
     float l2_ratio = 1.0f;
+    // strict mode: codewords whose smallest decision margin is below strict_tau are re-decoded in double
+    int* d_flag_list = nullptr;            // [flag_cap] codeword indices, filled by the fast kernel
+    int* d_flag_count = nullptr;           // [2]: counter of the current call, copy kept for polar_b200_get_info
+    int flag_cap = 0;
+    float strict_tau = 0.0f;
+    double* d_cvt = nullptr;               // float -> double conversion buffer of the kernels that take one input type
+    size_t cvt_bytes = 0;
+    long long last_flagged = -1;           // resolved lazily (device counter)
+    bool flagged_pending = false;
+    // one call in flight per ctx: every entry point makes its stream wait for the previous call's last launch
+    cudaEvent_t ev_last = nullptr;
+    cudaStream_t last_stream = nullptr;
+    bool have_last = false;
+    // host-side staging of the strict double entry point
+    float* h_f32 = nullptr; size_t h_f32_bytes = 0;
+    int* h_list = nullptr; size_t h_list_bytes = 0;
+    double* h_gather = nullptr; size_t h_gather_bytes = 0;
+    uint32_t* h_out2 = nullptr; size_t h_out2_bytes = 0;
     long long launches = 0;
     int last_wpb = 0, last_blocks = 0, last_smem = 0, last_kernel = 0;
     size_t scratch_bytes = 0;
@@ -536,13 +555,13 @@ struct LaunchPlan {
 
 // Decide which layers live in shared memory. Layers lamS..n-1 of the LLR tree
 // (2^(n-lamS+1) - 2 rows) and the partial-sum layers >= max(lamS,1) go to shared memory.
-LaunchPlan make_plan(const polar_b200_ctx* c, int elem = 4) {
+LaunchPlan make_plan(const polar_b200_ctx* c, int elem = 4, int warps_per_sm_override = 0) {
     const int rowb = 32 * elem;                       // bytes of one LLR row
     LaunchPlan p;
     memset(&p, 0, sizeof(p));
     const int n = c->n;
     p.wpb = env_int("POLAR_B200_WPB", 4);
-    const int warps_per_sm = env_int("POLAR_B200_WARPS_PER_SM", 16);
+    const int warps_per_sm = warps_per_sm_override > 0 ? warps_per_sm_override : env_int("POLAR_B200_WARPS_PER_SM", 16);
     if (p.wpb < 1) p.wpb = 1;
     if (p.wpb > 8) p.wpb = 8;
     int blocks_per_sm = warps_per_sm / p.wpb;
@@ -575,20 +594,27 @@ LaunchPlan make_plan(const polar_b200_ctx* c, int elem = 4) {
     return p;
 }
 
+// Scratch of the generic kernel: grow-only by bytes (the strides travel with every launch, so plans with different
+// layer splits or element types share the two buffers; a launch still running on another stream is ordered by the
+// ctx's one-call-in-flight rule before anything is freed -- cudaFree synchronises the device).
 int ensure_scratch(polar_b200_ctx* c, const LaunchPlan& p, int elem = 4) {
     const int warps = p.blocks * p.wpb;
-    if (c->d_gx && c->scratch_warps >= warps && c->scratch_lamS == p.lamS && c->scratch_elem == elem) return 0;
-    if (c->d_gx) cudaFree(c->d_gx);
-    if (c->d_gs) cudaFree(c->d_gs);
-    c->d_gx = nullptr; c->d_gs = nullptr;
     c->gx_stride = (p.gx_rows ? p.gx_rows : 1) * 32;
     c->gs_stride = (p.gs_rows ? p.gs_rows : 1) * 32;
-    CU_TRY(cudaMalloc(&c->d_gx, c->gx_stride * warps * elem));
-    CU_TRY(cudaMalloc(&c->d_gs, c->gs_stride * warps * sizeof(uint32_t)));
-    c->scratch_warps = warps;
-    c->scratch_lamS = p.lamS;
-    c->scratch_elem = elem;
-    c->scratch_bytes = (c->gx_stride * elem + c->gs_stride * sizeof(uint32_t)) * warps;
+    const size_t need_gx = c->gx_stride * warps * elem, need_gs = c->gs_stride * warps * sizeof(uint32_t);
+    if (need_gx > c->gx_bytes) {
+        if (c->d_gx) cudaFree(c->d_gx);
+        c->d_gx = nullptr; c->gx_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_gx, need_gx));
+        c->gx_bytes = need_gx;
+    }
+    if (need_gs > c->gs_bytes) {
+        if (c->d_gs) cudaFree(c->d_gs);
+        c->d_gs = nullptr; c->gs_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_gs, need_gs));
+        c->gs_bytes = need_gs;
+    }
+    c->scratch_bytes = c->gx_bytes + c->gs_bytes;
     return 0;
 }
 
@@ -635,14 +661,17 @@ int pick_fast_variant(const polar_b200_ctx* c, int L, int B) {
     return -1;
 }
 
-template <class Real>
-int decode_generic(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_packed, cudaStream_t st) {
-    LaunchPlan p = make_plan(c, (int)sizeof(Real));
+// list / count (device, may be null): decode only the listed codewords (strict mode's re-decode); B is then the capacity
+// of the list and the grid is sized for a handful of codewords per SM (the count is not known on the host).
+template <class Real, class In = Real>
+int decode_generic(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* info_packed, cudaStream_t st,
+                   const int* list = nullptr, const int* count = nullptr) {
+    LaunchPlan p = make_plan(c, (int)sizeof(Real), list ? env_int("POLAR_B200_REDECODE_WARPS_PER_SM", 8) : 0);
     int rc = ensure_scratch(c, p, (int)sizeof(Real));
     if (rc) return rc;
-    DecodeArgsT<Real> a;
+    DecodeArgsT<Real, In> a;
     memset(&a, 0, sizeof(a));
-    a.llr = llr; a.out = info_packed;
+    a.llr = llr; a.out = info_packed; a.list = list; a.count = count;
     a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = static_cast<Real*>(c->d_gx); a.gs = c->d_gs; a.gx_stride = c->gx_stride; a.gs_stride = c->gs_stride;
     a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.L = L;
@@ -654,8 +683,8 @@ int decode_generic(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* i
     int blocks = p.blocks;
     const int need_blocks = (groups + p.wpb - 1) / p.wpb;
     if (blocks > need_blocks) blocks = need_blocks;
-    CU_TRY(cudaFuncSetAttribute(scl_decode_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
-    scl_decode_kernel<Real><<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
+    CU_TRY(cudaFuncSetAttribute(scl_decode_kernel<Real, In>, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem_bytes));
+    scl_decode_kernel<Real, In><<<blocks, p.wpb * 32, p.smem_bytes, st>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     c->last_wpb = p.wpb; c->last_blocks = blocks; c->last_smem = p.smem_bytes;
@@ -755,7 +784,10 @@ int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_
     return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
-int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st) {
+// margin (device, [>= cw_base + B], may be null) / flags: see fast::Args. cw_base = index of llr's first row in the caller's
+// batch (the host entry point decodes chunk by chunk but keeps one flag list).
+int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st,
+                float* margin = nullptr, int* flag_list = nullptr, int* flag_count = nullptr, float tau = 0.0f, int cw_base = 0) {
     const FastVariant& v = kFastVariants[variant];
     int blocks = c->sm_count * v.bps;
     const int warps = blocks * v.wpb;
@@ -798,6 +830,7 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     fast::Args a;
     a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = c->d_fgx; a.gs = c->d_fgs; a.B = B; a.K = c->K; a.crc = c->crc; a.L = L;
+    a.margin = margin; a.flag_list = flag_list; a.flag_count = flag_count; a.tau = tau; a.cw_base = cw_base;
     {
         // leading frozen leaves handled by the cooperative phase (whole 16-leaf blocks below layer T's first node)
         const int mt = (1 << v.nlog) >> v.T;
@@ -824,6 +857,207 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     c->last_wpb = v.wpb; c->last_blocks = blocks; c->last_smem = v.smem_per_warp * v.wpb; c->last_kernel = 1 + variant;
+    return POLAR_B200_OK;
+}
+
+
+// ---- one call in flight per ctx (the scratch buffers are per ctx): a call on another stream than the previous one
+// first waits for the previous call's last launch ----
+int call_begin(polar_b200_ctx* c, cudaStream_t st) {
+    if (!c->ev_last) CU_TRY(cudaEventCreateWithFlags(&c->ev_last, cudaEventDisableTiming));
+    if (c->have_last && c->last_stream != st) CU_TRY(cudaStreamWaitEvent(st, c->ev_last, 0));
+    return 0;
+}
+int call_end(polar_b200_ctx* c, cudaStream_t st) {
+    CU_TRY(cudaEventRecord(c->ev_last, st));
+    c->last_stream = st; c->have_last = true;
+    return 0;
+}
+// wait for everything this ctx has queued (error paths, buffer growth)
+void drain(polar_b200_ctx* c) {
+    if (c->st_h2d) { cudaStreamSynchronize(c->st_h2d); cudaStreamSynchronize(c->st_run); cudaStreamSynchronize(c->st_d2h); }
+    if (c->have_last) cudaEventSynchronize(c->ev_last);
+}
+int grow_host(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr; *cap = 0;
+    CU_TRY(cudaMallocHost(p, need));
+    *cap = need;
+    return 0;
+}
+int ensure_flags(polar_b200_ctx* c, int B) {
+    if (!c->d_flag_count) CU_TRY(cudaMalloc(&c->d_flag_count, 2 * sizeof(int)));
+    if (B > c->flag_cap) {
+        if (c->d_flag_list) cudaFree(c->d_flag_list);
+        c->d_flag_list = nullptr; c->flag_cap = 0;
+        CU_TRY(cudaMalloc(&c->d_flag_list, (size_t)B * sizeof(int)));
+        c->flag_cap = B;
+    }
+    return 0;
+}
+
+__global__ void to_double_kernel(const float* in, double* out, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+// everything in double on float LLRs (reference precision: the reference itself widens its input to double)
+int decode_f64_from_float(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, cudaStream_t st) {
+    if (L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0)) {
+        const size_t nel = (size_t)B * c->N;
+        if (nel * sizeof(double) > c->cvt_bytes) {
+            if (c->d_cvt) cudaFree(c->d_cvt);
+            c->d_cvt = nullptr; c->cvt_bytes = 0;
+            CU_TRY(cudaMalloc(&c->d_cvt, nel * sizeof(double)));
+            c->cvt_bytes = nel * sizeof(double);
+        }
+        to_double_kernel<<<c->sm_count * 8, 256, 0, st>>>(llr, c->d_cvt, nel);
+        CU_TRY(cudaGetLastError());
+        c->launches += 1;
+        return decode_wide<double>(c, c->d_cvt, B, L, out, st);
+    }
+    return decode_generic<double, float>(c, llr, B, L, out, st);
+}
+
+float strict_tau(const polar_b200_ctx* c) {
+    const char* e = getenv("POLAR_B200_STRICT_TAU");
+    if (e && *e) return (float)atof(e);
+    return c->strict_tau;
+}
+
+// Device-resident decode in one of the three arithmetic modes (include/polar_b200.h). llr / out: device pointers.
+// cw_base / zero_count / redecode serve the chunked host entry point: chunks share one flag list and are re-decoded
+// together after the last chunk.
+int decode_mode(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, int mode, float* margin, cudaStream_t st,
+                int fv_forced = -2, int cw_base = 0, bool zero_count = true, bool redecode = true) {
+    // the fast kernels read the channel rows with 16-byte loads; anything else goes to the generic kernel (scalar loads)
+    const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
+    const int fv = !aligned ? -1 : (fv_forced >= -1 ? fv_forced : pick_fast_variant(c, L, B));
+    if (margin && fv < 0) return POLAR_B200_E_UNSUPPORTED;       // margins are reported by the fast kernels only
+    if (mode == POLAR_B200_MODE_FP32) {
+        if (fv >= 0) return decode_fast(c, fv, llr, B, L, out, st, margin);
+        return decode_any<float>(c, llr, B, L, out, st);
+    }
+    if (mode == POLAR_B200_MODE_F64 || fv < 0) return decode_f64_from_float(c, llr, B, L, out, st);
+    // strict: fp32 everywhere, double where a decision was closer than tau
+    int rc = ensure_flags(c, cw_base + B);
+    if (rc) return rc;
+    if (zero_count) CU_TRY(cudaMemsetAsync(c->d_flag_count, 0, sizeof(int), st));
+    rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, strict_tau(c), cw_base);
+    if (rc) return rc;
+    c->flagged_pending = true;
+    if (!redecode) return POLAR_B200_OK;
+    return decode_generic<double, float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count);
+}
+
+// Host memory in and out: the batch is cut into chunks whose H2D copy, decode and D2H copy overlap on three internal
+// streams. redecode_on_device = false (strict mode only): flags are left in d_flag_list / d_flag_count for the caller.
+int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32_t* info_packed_host, int mode,
+                  cudaStream_t user_stream, bool redecode_on_device) {
+    CU_TRY(cudaStreamSynchronize(user_stream));     // work queued by the caller comes first
+    if (!c->st_h2d) {
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_run, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
+        for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) {
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+            CU_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        }
+    }
+    int rc = call_begin(c, c->st_run);
+    if (rc) return rc;
+    c->have_last = false;                           // this call ends with everything synchronised
+    const bool strict = mode == POLAR_B200_MODE_STRICT;
+    int fv = pick_fast_variant(c, L, B);
+    if (mode == POLAR_B200_MODE_F64 || fv < 0 && (strict || L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0))) {
+        // double everywhere, wide lists, N > 8192: a single chunk on the run stream
+        CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, c->st_run));
+        rc = (mode == POLAR_B200_MODE_FP32) ? decode_wide<float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run)
+                                            : decode_f64_from_float(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
+        CU_TRY(cudaStreamSynchronize(c->st_run));
+        c->last_chunks = 1;
+        if (strict) { if ((rc = ensure_flags(c, 1))) return rc; CU_TRY(cudaMemset(c->d_flag_count, 0, sizeof(int))); }
+        return POLAR_B200_OK;
+    }
+    // Chunks are whole "rounds" of the persistent grid (every warp decodes the same number of
+    // codewords per chunk), so splitting costs no extra tail; about 6 chunks hide the PCIe time.
+    // The kernel variant is chosen for the chunk size (every launch is one chunk).
+    auto round_size = [&](int v) {
+        if (v >= 0) return c->sm_count * kFastVariants[v].bps * kFastVariants[v].wpb * (32 >> kFastVariants[v].wlog);
+        LaunchPlan p = make_plan(c, 4);
+        int W = 1; while (W < L) W <<= 1;
+        return p.blocks * p.wpb * (32 / W);
+    };
+    auto chunk_size = [&](int per_round) {
+        const int rounds = (B + per_round - 1) / per_round;
+        long long ch = (long long)((rounds + 5) / 6) * per_round;
+        if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || ch <= 0 || ch > B) ch = B;
+        return ch;
+    };
+    long long chunk = chunk_size(round_size(fv));
+    const int fv2 = pick_fast_variant(c, L, (int)chunk);
+    if (fv2 != fv) { fv = fv2; chunk = chunk_size(round_size(fv)); }
+    if (fv >= 0 && kFastVariants[fv].wlog <= 1 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1) {
+        // lists <= 2 decode at least twice as fast as PCIe delivers the LLRs (8 KB per codeword at N = 2048): the copy is the
+        // critical path, so cut the batch into six equal chunks even if that is less than one round of the grid --
+        // only the last chunk's decode is then exposed
+        fv = pick_fast_variant(c, L, (B + 5) / 6);
+        const int cpb = kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);     // codewords per block
+        chunk = (((long long)(B + 5) / 6 + cpb - 1) / cpb) * cpb;
+        if (chunk > B) chunk = B;
+    }
+    int nchunks = (int)((B + chunk - 1) / chunk);
+    if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
+    // chunk boundaries (in codewords). Equal chunks by default. With one codeword per warp (lists 17..32) decoding a
+    // round takes several times longer than copying it in, so the chunks grow geometrically instead (1, 4, 16, ...
+    // rounds): only the first, small copy is exposed, and there are fewer chunk boundaries, each of which is a
+    // grid-wide join where the fastest warps wait for the slowest.
+    long long bounds[polar_b200_ctx::kMaxChunks + 1];
+    bounds[0] = 0;
+    const bool geometric = fv >= 0 && kFastVariants[fv].wlog == 5 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1;
+    if (geometric) {
+        const long long per_round = round_size(fv);
+        long long rounds_in_chunk = 1;
+        nchunks = 0;
+        while (bounds[nchunks] < B && nchunks < polar_b200_ctx::kMaxChunks) {
+            long long hi = bounds[nchunks] + rounds_in_chunk * per_round;
+            if (hi > B || nchunks == polar_b200_ctx::kMaxChunks - 1) hi = B;
+            if (B - hi < per_round * rounds_in_chunk / 2) hi = B;       // no small leftover chunk
+            bounds[++nchunks] = hi;
+            rounds_in_chunk *= 4;
+        }
+    } else {
+        for (int i = 1; i <= nchunks; ++i) bounds[i] = ((long long)i * chunk < B) ? (long long)i * chunk : B;
+    }
+    c->last_chunks = nchunks;
+    const bool final_copy = strict && redecode_on_device;     // the re-decode rewrites rows of earlier chunks
+    if (strict && (rc = ensure_flags(c, B))) return rc;       // one flag list for all chunks: sized before the first launch
+    for (int i = 0; i < nchunks; ++i) {
+        const long long lo = bounds[i];
+        const int nb = (int)(bounds[i + 1] - lo);
+        float* d_in = c->d_llr_stage + (size_t)lo * c->N;
+        uint32_t* d_o = c->d_out_stage + (size_t)lo * c->KW;
+        CU_TRY(cudaMemcpyAsync(d_in, llr_host + (size_t)lo * c->N, (size_t)nb * c->N * sizeof(float),
+                               cudaMemcpyHostToDevice, c->st_h2d));
+        CU_TRY(cudaEventRecord(c->ev_in[i], c->st_h2d));
+        CU_TRY(cudaStreamWaitEvent(c->st_run, c->ev_in[i], 0));
+        rc = decode_mode(c, d_in, nb, L, d_o, mode, nullptr, c->st_run, fv, (int)lo, i == 0, false);
+        if (rc) return rc;
+        if (final_copy) continue;
+        CU_TRY(cudaEventRecord(c->ev_done[i], c->st_run));
+        CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_done[i], 0));
+        CU_TRY(cudaMemcpyAsync(info_packed_host + (size_t)lo * c->KW, d_o, (size_t)nb * c->KW * sizeof(uint32_t),
+                               cudaMemcpyDeviceToHost, c->st_d2h));
+    }
+    if (final_copy) {
+        rc = decode_generic<double, float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run, c->d_flag_list, c->d_flag_count);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
+        CU_TRY(cudaStreamSynchronize(c->st_run));
+    }
+    CU_TRY(cudaStreamSynchronize(c->st_d2h));
     return POLAR_B200_OK;
 }
 
@@ -876,6 +1110,7 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
     if (!c) return POLAR_B200_E_ARG;
     c->device = device; c->n = n; c->N = N; c->K = K; c->crc = crc_bits;
     c->max_list = max_list; c->max_batch = max_batch;
+    c->strict_tau = POLAR_B200_DEFAULT_STRICT_TAU;
     c->KW = (K + 31) / 32; c->NW = (N + 31) / 32;
     int rc = 0;
     auto fail = [&](int code) { polar_b200_destroy(c); return code; };
@@ -927,6 +1162,9 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
+    cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt);
+    cudaFreeHost(c->h_f32); cudaFreeHost(c->h_list); cudaFreeHost(c->h_gather); cudaFreeHost(c->h_out2);
+    if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->st_h2d) {
         cudaStreamDestroy(c->st_h2d); cudaStreamDestroy(c->st_run); cudaStreamDestroy(c->st_d2h);
         for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
@@ -937,112 +1175,98 @@ int polar_b200_destroy(polar_b200_ctx* c) {
 
 int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
                               uint32_t* info_packed, void* cuda_stream) {
+    return polar_b200_decode_scl_llr_ex(c, llr, B, L, info_packed, POLAR_B200_MODE_FP32, nullptr, cuda_stream);
+}
+
+int polar_b200_decode_scl_llr_ex(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* info_packed,
+                                 int mode, float* margin, void* cuda_stream) {
     if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
+    if (mode != POLAR_B200_MODE_FP32 && mode != POLAR_B200_MODE_STRICT && mode != POLAR_B200_MODE_F64) return POLAR_B200_E_ARG;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int fv = pick_fast_variant(c, L, B);
-    if (fv >= 0) return decode_fast(c, fv, llr, B, L, info_packed, st);
-    return decode_any<float>(c, llr, B, L, info_packed, st);
+    int rc = call_begin(c, st);
+    if (rc) return rc;
+    rc = decode_mode(c, llr, B, L, info_packed, mode, margin, st);
+    if (rc) return rc;
+    return call_end(c, st);
 }
 
 int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int B, int L,
                                    uint32_t* info_packed_host, void* cuda_stream) {
+    return polar_b200_decode_scl_llr_host_ex(c, llr_host, B, L, info_packed_host, POLAR_B200_MODE_FP32, cuda_stream);
+}
+
+int polar_b200_decode_scl_llr_host_ex(polar_b200_ctx* c, const float* llr_host, int B, int L,
+                                      uint32_t* info_packed_host, int mode, void* cuda_stream) {
     if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
-    if (B > c->max_batch) return POLAR_B200_E_BATCH;
+    if (mode != POLAR_B200_MODE_FP32 && mode != POLAR_B200_MODE_STRICT && mode != POLAR_B200_MODE_F64) return POLAR_B200_E_ARG;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
-    CU_TRY(cudaStreamSynchronize((cudaStream_t)cuda_stream));     // work queued by the caller comes first
-    if (!c->st_h2d) {
-        CU_TRY(cudaStreamCreateWithFlags(&c->st_h2d, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&c->st_run, cudaStreamNonBlocking));
-        CU_TRY(cudaStreamCreateWithFlags(&c->st_d2h, cudaStreamNonBlocking));
-        for (int i = 0; i < polar_b200_ctx::kMaxChunks; ++i) {
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
-            CU_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
-        }
-    }
-    // Chunks are whole "rounds" of the persistent grid (every warp decodes the same number of
-    // codewords per chunk), so splitting costs no extra tail; about 6 chunks hide the PCIe time.
-    // The kernel variant is chosen for the chunk size (every launch is one chunk).
-    auto round_size = [&](int fv) {
-        if (fv >= 0) return c->sm_count * kFastVariants[fv].bps * kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);
-        LaunchPlan p = make_plan(c, 4);
-        int W = 1; while (W < L) W <<= 1;
-        return p.blocks * p.wpb * (32 / W);
-    };
-    auto chunk_size = [&](int per_round) {
-        const int rounds = (B + per_round - 1) / per_round;
-        long long ch = (long long)((rounds + 5) / 6) * per_round;
-        if (env_int("POLAR_B200_HOST_CHUNKS", 1) == 0 || ch <= 0 || ch > B) ch = B;
-        return ch;
-    };
-    if (L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0)) {
-        // wide lists / N > 8192: one block per codeword, a single chunk on the run stream
-        CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, c->st_run));
-        int rc = decode_wide<float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
-        if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
-        CU_TRY(cudaStreamSynchronize(c->st_run));
-        c->last_chunks = 1;
-        return POLAR_B200_OK;
-    }
-    int fv = pick_fast_variant(c, L, B);
-    long long chunk = chunk_size(round_size(fv));
-    const int fv2 = pick_fast_variant(c, L, (int)chunk);
-    if (fv2 != fv) { fv = fv2; chunk = chunk_size(round_size(fv)); }
-    if (fv >= 0 && kFastVariants[fv].wlog <= 1 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1) {
-        // lists <= 2 decode at least twice as fast as PCIe delivers the LLRs (8 KB per codeword at N = 2048): the copy is the
-        // critical path, so cut the batch into six equal chunks even if that is less than one round of the grid --
-        // only the last chunk's decode is then exposed
-        fv = pick_fast_variant(c, L, (B + 5) / 6);
-        const int cpb = kFastVariants[fv].wpb * (32 >> kFastVariants[fv].wlog);     // codewords per block
-        chunk = (((long long)(B + 5) / 6 + cpb - 1) / cpb) * cpb;
-        if (chunk > B) chunk = B;
-    }
-    int nchunks = (int)((B + chunk - 1) / chunk);
-    if (nchunks > polar_b200_ctx::kMaxChunks) { nchunks = polar_b200_ctx::kMaxChunks; chunk = ((long long)B + nchunks - 1) / nchunks; }
-    // chunk boundaries (in codewords). Equal chunks by default. With one codeword per warp (lists 17..32) decoding a
-    // round takes several times longer than copying it in, so the chunks grow geometrically instead (1, 4, 16, ...
-    // rounds): only the first, small copy is exposed, and there are fewer chunk boundaries, each of which is a
-    // grid-wide join where the fastest warps wait for the slowest.
-    long long bounds[polar_b200_ctx::kMaxChunks + 1];
-    bounds[0] = 0;
-    const bool geometric = fv >= 0 && kFastVariants[fv].wlog == 5 && env_int("POLAR_B200_HOST_CHUNKS", 1) == 1;
-    if (geometric) {
-        const long long per_round = round_size(fv);
-        long long rounds_in_chunk = 1;
-        nchunks = 0;
-        while (bounds[nchunks] < B && nchunks < polar_b200_ctx::kMaxChunks) {
-            long long hi = bounds[nchunks] + rounds_in_chunk * per_round;
-            if (hi > B || nchunks == polar_b200_ctx::kMaxChunks - 1) hi = B;
-            if (B - hi < per_round * rounds_in_chunk / 2) hi = B;       // no small leftover chunk
-            bounds[++nchunks] = hi;
-            rounds_in_chunk *= 4;
-        }
-    } else {
-        for (int i = 1; i <= nchunks; ++i) bounds[i] = ((long long)i * chunk < B) ? (long long)i * chunk : B;
-    }
-    c->last_chunks = nchunks;
-    for (int i = 0; i < nchunks; ++i) {
-        const long long lo = bounds[i];
-        const int nb = (int)(bounds[i + 1] - lo);
-        float* d_in = c->d_llr_stage + (size_t)lo * c->N;
-        uint32_t* d_o = c->d_out_stage + (size_t)lo * c->KW;
-        CU_TRY(cudaMemcpyAsync(d_in, llr_host + (size_t)lo * c->N, (size_t)nb * c->N * sizeof(float),
-                               cudaMemcpyHostToDevice, c->st_h2d));
-        CU_TRY(cudaEventRecord(c->ev_in[i], c->st_h2d));
-        CU_TRY(cudaStreamWaitEvent(c->st_run, c->ev_in[i], 0));
-        int rc = fv >= 0 ? decode_fast(c, fv, d_in, nb, L, d_o, c->st_run) : decode_generic<float>(c, d_in, nb, L, d_o, c->st_run);
-        if (rc) return rc;
-        CU_TRY(cudaEventRecord(c->ev_done[i], c->st_run));
-        CU_TRY(cudaStreamWaitEvent(c->st_d2h, c->ev_done[i], 0));
-        CU_TRY(cudaMemcpyAsync(info_packed_host + (size_t)lo * c->KW, d_o, (size_t)nb * c->KW * sizeof(uint32_t),
-                               cudaMemcpyDeviceToHost, c->st_d2h));
-    }
-    CU_TRY(cudaStreamSynchronize(c->st_d2h));
+    int rc = polar_b200_reserve(c, B);
+    if (rc) return rc;
+    rc = host_pipeline(c, llr_host, B, L, info_packed_host, mode, (cudaStream_t)cuda_stream, true);
+    if (rc) drain(c);                  // no copy into the caller's buffers may still be in flight when an error is returned
+    return rc;
+}
+
+int polar_b200_decode_scl_llr_f64_strict_host(polar_b200_ctx* c, const double* llr_host, int B, int L,
+                                              uint32_t* info_packed_host, void* cuda_stream) {
+    if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
+    if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
+    if (B == 0) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    if (pick_fast_variant(c, L, B) < 0)  // no margin-reporting kernel for this (n, list): everything in double
+        return polar_b200_decode_scl_llr_f64_host(c, llr_host, B, L, info_packed_host, cuda_stream);
+    int rc = polar_b200_reserve(c, B);
+    if (rc) return rc;
+    const size_t nel = (size_t)B * c->N;
+    if ((rc = grow_host((void**)&c->h_f32, &c->h_f32_bytes, nel * sizeof(float)))) return rc;
+    for (size_t i = 0; i < nel; ++i) c->h_f32[i] = (float)llr_host[i];
+    // stage 1: fp32 decode of everything, flags only (the re-decode needs the caller's doubles)
+    rc = host_pipeline(c, c->h_f32, B, L, info_packed_host, POLAR_B200_MODE_STRICT, (cudaStream_t)cuda_stream, false);
+    if (rc) { drain(c); return rc; }
+    int nf = 0;
+    CU_TRY(cudaMemcpy(&nf, c->d_flag_count, sizeof(int), cudaMemcpyDeviceToHost));
+    c->last_flagged = nf; c->flagged_pending = false;
+    if (nf == 0) return POLAR_B200_OK;
+    if ((rc = grow_host((void**)&c->h_list, &c->h_list_bytes, (size_t)nf * sizeof(int)))) return rc;
+    if ((rc = grow_host((void**)&c->h_gather, &c->h_gather_bytes, (size_t)nf * c->N * sizeof(double)))) return rc;
+    if ((rc = grow_host((void**)&c->h_out2, &c->h_out2_bytes, (size_t)nf * c->KW * sizeof(uint32_t)))) return rc;
+    CU_TRY(cudaMemcpy(c->h_list, c->d_flag_list, (size_t)nf * sizeof(int), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < nf; ++i)
+        memcpy(c->h_gather + (size_t)i * c->N, llr_host + (size_t)c->h_list[i] * c->N, (size_t)c->N * sizeof(double));
+    // stage 2: the flagged codewords again, in double on the caller's double LLRs
+    rc = polar_b200_decode_scl_llr_f64_host(c, c->h_gather, nf, L, c->h_out2, cuda_stream);
+    if (rc) return rc;
+    for (int i = 0; i < nf; ++i)
+        memcpy(info_packed_host + (size_t)c->h_list[i] * c->KW, c->h_out2 + (size_t)i * c->KW, (size_t)c->KW * sizeof(uint32_t));
+    return POLAR_B200_OK;
+}
+
+int polar_b200_reserve(polar_b200_ctx* c, int max_batch) {
+    if (!c || max_batch < 1) return POLAR_B200_E_ARG;
+    if (max_batch <= c->max_batch) return POLAR_B200_OK;
+    CU_TRY(cudaSetDevice(c->device));
+    drain(c);                                             // the old staging buffers may still be in use
+    float* nl = nullptr; uint32_t* no = nullptr;
+    CU_TRY(cudaMalloc(&nl, (size_t)max_batch * c->N * sizeof(float)));
+    cudaError_t e = cudaMalloc(&no, (size_t)max_batch * c->KW * sizeof(uint32_t));
+    if (e != cudaSuccess) { cudaFree(nl); return (int)e; }
+    cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
+    c->d_llr_stage = nl; c->d_out_stage = no;
+    // staging of the double / probability-domain host entry points is sized by max_batch too: reallocated on next use
+    cudaFree(c->d_llr64_stage); c->d_llr64_stage = nullptr;
+    cudaFree(c->d_prob_stage); c->d_prob_stage = nullptr;
+    c->max_batch = max_batch;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_set_strict_tau(polar_b200_ctx* c, float tau) {
+    if (!c || !(tau >= 0.0f)) return POLAR_B200_E_ARG;
+    c->strict_tau = tau;
     return POLAR_B200_OK;
 }
 
@@ -1052,23 +1276,30 @@ int polar_b200_decode_scl_llr_f64(polar_b200_ctx* c, const double* llr, int B, i
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
-    return decode_any<double>(c, llr, B, L, info_packed, (cudaStream_t)cuda_stream);
+    int rc = call_begin(c, (cudaStream_t)cuda_stream);
+    if (rc) return rc;
+    rc = decode_any<double>(c, llr, B, L, info_packed, (cudaStream_t)cuda_stream);
+    if (rc) return rc;
+    return call_end(c, (cudaStream_t)cuda_stream);
 }
 
 int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* c, const double* llr_host, int B, int L,
                                        uint32_t* info_packed_host, void* cuda_stream) {
     if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
-    if (B > c->max_batch) return POLAR_B200_E_BATCH;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
+    { const int rr = polar_b200_reserve(c, B); if (rr) return rr; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = call_begin(c, st);
+    if (rc) return rc;
     if (!c->d_llr64_stage) CU_TRY(cudaMalloc(&c->d_llr64_stage, (size_t)c->max_batch * c->N * sizeof(double)));
     CU_TRY(cudaMemcpyAsync(c->d_llr64_stage, llr_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = decode_any<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
-    if (rc) return rc;
+    rc = decode_any<double>(c, c->d_llr64_stage, B, L, c->d_out_stage, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
     CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    c->have_last = false;
     return POLAR_B200_OK;
 }
 
@@ -1078,27 +1309,34 @@ int polar_b200_decode_scl_p1(polar_b200_ctx* c, const double* p1, const double* 
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
-    return decode_prob(c, p0, p1, B, L, info_packed, (cudaStream_t)cuda_stream);
+    int rc = call_begin(c, (cudaStream_t)cuda_stream);
+    if (rc) return rc;
+    rc = decode_prob(c, p0, p1, B, L, info_packed, (cudaStream_t)cuda_stream);
+    if (rc) return rc;
+    return call_end(c, (cudaStream_t)cuda_stream);
 }
 
 int polar_b200_decode_scl_p1_host(polar_b200_ctx* c, const double* p1_host, const double* p0_host, int B, int L,
                                   uint32_t* info_packed_host, void* cuda_stream) {
     if (!c || !p1_host || !p0_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
-    if (B > c->max_batch) return POLAR_B200_E_BATCH;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
+    { const int rr = polar_b200_reserve(c, B); if (rr) return rr; }
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const size_t per = (size_t)c->max_batch * c->N;
+    int rc = call_begin(c, st);
+    if (rc) return rc;
     if (!c->d_prob_stage) CU_TRY(cudaMalloc(&c->d_prob_stage, 2 * per * sizeof(double)));
     double* d_p0 = c->d_prob_stage;
     double* d_p1 = c->d_prob_stage + per;
     CU_TRY(cudaMemcpyAsync(d_p0, p0_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_p1, p1_host, (size_t)B * c->N * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = decode_prob(c, d_p0, d_p1, B, L, c->d_out_stage, st);
-    if (rc) return rc;
+    rc = decode_prob(c, d_p0, d_p1, B, L, c->d_out_stage, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
     CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    c->have_last = false;
     return POLAR_B200_OK;
 }
 
@@ -1148,6 +1386,15 @@ long long polar_b200_get_info(polar_b200_ctx* c, int key) {
         case POLAR_B200_INFO_SCRATCH_BYTES: return (long long)c->scratch_bytes;
         case POLAR_B200_INFO_KERNEL_KIND: return c->last_kernel;
         case POLAR_B200_INFO_HOST_CHUNKS: return c->last_chunks;
+        case POLAR_B200_INFO_LAST_FLAGGED:
+            if (c->flagged_pending) {
+                int nf = 0;
+                cudaSetDevice(c->device);
+                drain(c);
+                if (cudaMemcpy(&nf, c->d_flag_count, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+                c->last_flagged = nf; c->flagged_pending = false;
+            }
+            return c->last_flagged;
         default: return -1;
     }
 }

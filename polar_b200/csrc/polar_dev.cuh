@@ -18,10 +18,12 @@ constexpr int kMaxN = 15;          // the reference's own limit: block length is
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-template <class Real>
+template <class Real, class In = Real>
 struct DecodeArgsT {
-    const Real* llr;             // [B][N]
+    const In* llr;               // [B][N] (converted to Real on load)
     uint32_t* out;               // [B][KW]
+    const int* list;             // null, or the codeword indices to decode (strict mode's re-decode of flagged codewords)
+    const int* count;            // with `list`: number of entries (device memory, written by the kernel before this one)
     const uint32_t* frozen_words;// [max(1,N/32)], bit phi set = frozen
     const uint16_t* info_order;  // [K + crc]
     const uint32_t* crc_masks;   // [crc][NW] over phi

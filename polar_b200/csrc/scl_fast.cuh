@@ -64,7 +64,7 @@ struct Cfg {
     static constexpr bool TM = TM_ != 0;
     static constexpr int LT = LAMS - 1;
     static constexpr int TM_COLS = TM ? ((N >> LT) < 32 ? 32 : (N >> LT)) : 0;
-    static_assert(!TM || (LT >= T && (N >> LT) <= 128), "TMEM layer must lie in [T, LAMS) and have <= 128 rows");
+    static_assert(!TM || (LT >= T && (N >> LT) <= 256), "TMEM layer must lie in [T, LAMS) and have <= 256 rows");
     static constexpr int GX_ROWS = rows(T, TM ? LT : LAMS);   // HBM scratch rows (32 floats each)
     static constexpr int SX_ROWS = rows(LAMS, LB);     // shared rows (layers LAMS..NLOG-5)
     static constexpr int XS_FLOATS = N - MT;           // shared compact arrays XS_1..XS_T
@@ -84,7 +84,8 @@ struct Cfg {
     static constexpr __host__ __device__ int ss_rows() { int r = 0; for (int j = 1; j <= SWL; ++j) if (!s_global(j)) r += swords(j); return r; }
     static constexpr int GS_ROWS = gs_rows();
     static constexpr int SS_ROWS = ss_rows();
-    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64;
+    // + 64 bytes of clone scatter / free-path stack, + 128 bytes of decision-margin slots (one per codeword of the warp)
+    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64 + 128;
     static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
     // lists <= 16 (G > 1 codewords per warp): the channel LLRs of the warp's codewords are staged TRANSPOSED
     // ([position / 4][codeword][4], so that a lane still reads float4) behind the XS arrays, which are stored
@@ -107,6 +108,14 @@ struct Args {
     uint32_t* gs;
     int B, K, crc, L;
     int PA;            // leading frozen leaves decoded cooperatively (multiple of 16, < N >> T)
+    // decision margins (strict mode): the smallest gap any keep/drop decision of a codeword was
+    // taken with. margin (may be null): [B] floats out. flag_list / flag_count (may be null): codewords whose margin
+    // is below tau are appended (atomic counter) for re-decoding in reference precision.
+    float* margin;
+    int* flag_list;
+    int* flag_count;
+    float tau;
+    int cw_base;       // index of llr's row 0 in the caller's batch (margin / flag_list are indexed by batch position)
 };
 
 struct Warp {          // per-warp pointers
@@ -123,6 +132,7 @@ struct Warp {          // per-warp pointers
     float* xst;        // lists <= 16: XS arrays of the warp's codewords, transposed [index][codeword]
     float* cht;        // lists <= 16: channel LLRs of the warp's codewords, transposed [position][codeword]
     int g;             // lists <= 16: this lane's codeword within the warp
+    uint32_t* mg;      // shared: smallest decision margin so far (float bits, >= 0), one slot per codeword of the warp
 };
 
 struct Lane {          // per-path state
@@ -169,6 +179,13 @@ template <int W> __device__ __forceinline__ unsigned gballot(bool p, int gbase) 
 }
 template <class P> __device__ __forceinline__ P* shfl_ptr(P* p, int src) {
     return reinterpret_cast<P*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(p), src));
+}
+
+// Decision margin: the gap (>= 0) between the worst fork that was kept and the best fork that was dropped. A gap
+// below the arithmetic's own error means the double-precision reference may decide otherwise; such codewords are
+// re-decoded in double (strict mode). Non-negative floats order like their bit patterns; NaN (inf - inf) sorts last.
+template <int W> __device__ __forceinline__ void note_margin(const Warp& w, float gap) {
+    if ((w.lane & (W - 1)) == 0) atomicMin(w.mg + w.g, __float_as_uint(gap));
 }
 
 // ---- tensor memory as a per-warp scratch (tcgen05.ld/st, shape 32x32b: lane i of the warp <-> TMEM lane i of
@@ -920,6 +937,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     if constexpr (W == 1) {
         // plain SC (list 1): the better of the two forks survives, fork 0 on a tie (index order, PolarCode.cpp:543-553)
         if (s.active) s.pm = like1 ? m1 : m0;
+        note_margin<W>(w, ax);                              // the decision is the sign of the leaf LLR
         return like1 ? 1u : 0u;
     }
     if constexpr (W == 32) {
@@ -930,29 +948,37 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 const unsigned ka = gmax<W>(s.active ? klo : 0u);
                 if (kb > ka) {
                     if (s.active) s.pm = mlo;
+                    note_margin<W>(w, __uint_as_float(kb) - __uint_as_float(ka));
                     return like1 ? 1u : 0u;
                 }
             }
             const unsigned lk = __ballot_sync(FULL_MASK, like1);
             unsigned keptA = act, keptB = 0;
             int count = A;
+            // margin bookkeeping: last promoted / last demoted metric, and the pair the loop stopped at
+            float kbl = -CUDART_INF_F, kal = CUDART_INF_F, kbn = CUDART_INF_F, kan = -CUDART_INF_F;
             while (true) {
                 const unsigned candB = act & ~keptB;
-                if (candB == 0) break;
+                if (candB == 0) {                          // every unlikely fork was kept
+                    kan = __uint_as_float(gmax<W>(((keptA >> lane) & 1u) ? klo : 0u));
+                    break;
+                }
                 const unsigned kb = gmin<W>(((candB >> lane) & 1u) ? khi : 0xFFFFFFFFu);
                 const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
                 const int bl = __ffs(eqb) - 1;             // lowest lane = lowest fork index among equals
-                if (count < L) { keptB |= 1u << bl; ++count; continue; }
+                if (count < L) { keptB |= 1u << bl; ++count; kbl = __uint_as_float(kb); continue; }
                 const unsigned ka = gmax<W>(((keptA >> lane) & 1u) ? klo : 0u);
                 const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
                 const int al = 31 - __clz(eqa);            // highest lane = highest fork index among equals
                 const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
                 const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
                 const bool better = (kb < ka) || (kb == ka && idxb < idxa);
-                if (!better) break;
+                if (!better) { kbn = __uint_as_float(kb); kan = __uint_as_float(ka); break; }
                 keptB |= 1u << bl;
                 keptA &= ~(1u << al);
+                kbl = __uint_as_float(kb); kal = __uint_as_float(ka);
             }
+            note_margin<W>(w, fminf(kbn, kal) - fmaxf(kan, kbl));   // best dropped fork - worst kept fork
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -963,9 +989,9 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
         unsigned keptA = act, keptB = 0;
         int count = A;
         bool done = !(2 * A > L);
+        float kbl = -CUDART_INF_F, kal = CUDART_INF_F, kbn = CUDART_INF_F, kan = -CUDART_INF_F;   // as above
         while (true) {
             const unsigned candB = act & ~keptB;
-            if (!done && candB == 0) done = true;
             if (!__any_sync(FULL_MASK, !done)) break;
             const bool cb = (candB >> slot) & 1u, ca = (keptA >> slot) & 1u;
             const unsigned kb = gmin<W>(cb ? khi : 0xFFFFFFFFu);
@@ -973,19 +999,23 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             const unsigned ka = gmax<W>(ca ? klo : 0u);
             const unsigned eqa = gballot<W>(ca && klo == ka, gbase);
             if (!done) {
-                const int bl = __ffs(eqb) - 1;
-                if (count < L) { keptB |= 1u << bl; ++count; }
+                if (candB == 0) { done = true; kan = __uint_as_float(ka); }       // every unlikely fork was kept
                 else {
-                    const int al = 31 - __clz(eqa);
-                    const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
-                    const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
-                    const bool better = (kb < ka) || (kb == ka && idxb < idxa);
-                    if (!better) done = true;
-                    else { keptB |= 1u << bl; keptA &= ~(1u << al); }
+                    const int bl = __ffs(eqb) - 1;
+                    if (count < L) { keptB |= 1u << bl; ++count; kbl = __uint_as_float(kb); }
+                    else {
+                        const int al = 31 - __clz(eqa);
+                        const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
+                        const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
+                        const bool better = (kb < ka) || (kb == ka && idxb < idxa);
+                        if (!better) { done = true; kbn = __uint_as_float(kb); kan = __uint_as_float(ka); }
+                        else { keptB |= 1u << bl; keptA &= ~(1u << al); kbl = __uint_as_float(kb); kal = __uint_as_float(ka); }
+                    }
                 }
             }
         }
         if (2 * A > L) {
+            note_margin<W>(w, fminf(kbn, kal) - fmaxf(kan, kbl));
             const bool ka_ = (keptA >> slot) & 1u, kb_ = (keptB >> slot) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1109,6 +1139,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     w.ss = reinterpret_cast<uint32_t*>(my + C::SX_ROWS * 128);
     w.srcof = my + (C::SX_ROWS + C::SS_ROWS) * 128;
     w.stack = w.srcof + 32;
+    w.mg = reinterpret_cast<uint32_t*>(w.stack + 32);
     constexpr int W = C::W, G = C::G;
     w.tm = 0;
     // NQ warps share one SM sub-partition (warp index mod 4), i.e. one L0 instruction cache and one TMEM lane quadrant
@@ -1159,6 +1190,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         s.active = valid && (slot == c0);
         s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0;
         w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
+        w.mg[lane] = 0x7F800000u;                       // decision margin so far: +inf
         __syncwarp();
         int sp = L - 1;
         float lam_n = 0.0f;
@@ -1371,6 +1403,18 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         const int win = cand ? (__ffs(cand) - 1) : 0;
         const bool win_active = (act >> win) & 1u;
         __syncwarp();
+        if (a.margin != nullptr || a.flag_list != nullptr) {
+            // the final pick is a decision too: runner-up metric - winner's metric (0 when two paths tie)
+            float mgv = __uint_as_float(w.mg[w.g]);
+            if constexpr (W > 1) {
+                const unsigned second = gmin<W>((eligible && slot != win) ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
+                if (cand != 0 && second != 0xFFFFFFFFu) mgv = fminf(mgv, __uint_as_float(second) - __uint_as_float(best));
+            }
+            if (slot == 0 && valid) {
+                if (a.margin != nullptr) a.margin[a.cw_base + cw] = mgv;
+                if (a.flag_list != nullptr && mgv < a.tau) a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;
+            }
+        }
 #pragma unroll 1
         for (int g = 0; g < G; ++g) {
             const int cwg = grp * G + g;
