@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- codewords/s of the LLR-domain SCL polar decoder (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c2|c3|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c4|c1|c2|c3|c5] [--mode strict|fp32]
 
 A "step" is one pass of the hot path (decode_scl_llr) over one batch of synthetic BPSK/AWGN
 codewords. Default workload = BASELINE.json configs[3], the one the metric is quoted on:
@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 
 CONFIGS = {
     # name: (n, K, crc, L, sweep of Eb/N0 in dB, BASELINE.json index)
+    "c1": (9, 256, 0, 1, (2.0,), 0),
     "c2": (11, 1024, 0, 1, (2.0,), 1),
     "c3": (11, 1024, 16, 4, (2.0,), 2),
     "c4": (11, 1024, 16, 32, (1.0, 1.25, 1.5, 1.75, 2.0, 2.25, 2.5), 3),
@@ -56,6 +57,17 @@ def recorded_traffic(cfg, batch):
         return d["dram_bytes_per_codeword"] * batch, d
     except Exception:
         return None, None
+
+
+def wilson(err, n, z=1.96):
+    """95 % Wilson interval of a binomial proportion"""
+    if n == 0:
+        return [None, None]
+    p = err / n
+    den = 1 + z * z / n
+    c = (p + z * z / (2 * n)) / den
+    h = z * np.sqrt(p * (1 - p) / n + z * z / (4 * n * n)) / den
+    return [float(max(0.0, c - h)), float(min(1.0, c + h))]
 
 
 def issue_roofline(src, cw_per_s_per_gpu, sm_count, clocks):
@@ -151,15 +163,40 @@ def cpu_decoder(n, K, crc):
     return "port", oracle_lib.Port(n, K, 0.32, crc)
 
 
-def time_cpu(dec, llr, L, threads, budget_s):
-    """decode a bounded sample sized for ~budget_s seconds; returns (cw/s, sample size)."""
+def cpu_decoder_o3(n, K, crc):
+    """the same reference sources at -O3 -march=native, or None where the build is
+    absent or this host lacks an ISA extension it was compiled for"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib
+    if oracle_lib.have_ref_o3():
+        return oracle_lib.Ref(n, K, 0.32, crc, so=oracle_lib.REF_O3_SO)
+    return None
+
+
+def cpu_table(dec, dec_o3, llr, L, threads, seconds):
+    """SURVEY.md section 8(d)'s baseline table: 1 thread and all host threads, -O2 and -O3 -march=native, each on a
+    bounded sample of the same batch (at least 200 / 500 / 2000 codewords per thread for lists 32 / 4 / 1 when the
+    time budget allows)."""
+    rows = []
+    for name, d in (("-O2", dec), ("-O3 -march=native", dec_o3)):
+        if d is None:
+            rows.append({"build": name, "unavailable": "not prebuilt, or this host lacks an ISA extension it needs"})
+            continue
+        for th in sorted({1, threads}):
+            v, S = time_cpu(d, llr, L, th, seconds)
+            rows.append({"build": "g++ " + name, "threads": th, "value": v, "unit": "codewords/s", "sample_codewords": S})
+    return rows
+
+
+def time_cpu(dec, llr, L, threads, budget_s, want_out=False):
+    """decode a bounded sample sized for ~budget_s seconds; returns (cw/s, sample size[, decoded bits])."""
     probe = min(len(llr), max(threads, 8))
     t0 = time.perf_counter(); dec.decode_batch(llr[:probe], L, threads); t = time.perf_counter() - t0
     rate = probe / max(t, 1e-6)
     S = int(min(len(llr), max(threads, rate * budget_s)))
     S = max(threads, (S // threads) * threads)
-    t0 = time.perf_counter(); dec.decode_batch(llr[:S], L, threads); t = time.perf_counter() - t0
-    return S / t, S
+    t0 = time.perf_counter(); out = dec.decode_batch(llr[:S], L, threads); t = time.perf_counter() - t0
+    return (S / t, S, out) if want_out else (S / t, S)
 
 
 def run_reference(args):
@@ -200,7 +237,7 @@ def run_reference(args):
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from polar_b200 import PolarCode, bler, synth
+    from polar_b200 import PolarCode, bler, synth, pack_bits, unpack_bits
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -213,18 +250,20 @@ def run_ours(args):
 
     n, K, crc, L, sweep, _ = CONFIGS[args.config]
     N, B = 1 << n, args.batch
-    code = PolarCode(n, K, 0.32, crc, device=local)
+    mode = args.mode                                  # arithmetic of the headline arm (default: strict)
+    other = "fp32" if mode != "fp32" else "strict"
+    code = PolarCode(n, K, 0.32, crc, device=local, mode=mode)
     KW = code.KW
 
     # this rank's shard of the global batch (weak scaling: B codewords per GPU), pinned on the host
     h_llr = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
     h_out = torch.empty((B, KW), dtype=torch.int32, pin_memory=True)
     info, _ = synth.make_shard(code, SEED, rank * B, B, sweep=sweep, out_llr=h_llr.numpy())
-    from polar_b200 import pack_bits
     d_truth = torch.from_numpy(pack_bits(info).view(np.int32)).to(dev)
     d_llr = h_llr.to(dev)
     d_out = torch.empty((B, KW), dtype=torch.int32, device=dev)
-    d_nerr = torch.zeros(1, dtype=torch.int64, device=dev)
+    d_out2 = torch.empty((B, KW), dtype=torch.int32, device=dev)
+    d_berr = torch.zeros(B, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
 
     def barrier():
@@ -232,7 +271,15 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- device-resident arm ----
+    def timed(m, steps, out):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            code.decode_device(d_llr, L, out=out, mode=m)
+        e1.record(stream)
+        return e0, e1
+
+    # ---- device-resident arm (headline mode) ----
     sampler = ClockSampler(local)
     sampler.start()
     for _ in range(args.warmup):
@@ -240,18 +287,33 @@ def run_ours(args):
     launches0 = code.kernel_launches
     barrier()
     sampler.mark_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        code.decode_device(d_llr, L, out=d_out)
-    e1.record(stream)
+    e0, e1 = timed(mode, args.steps, d_out)
     barrier()
     sampler.mark_end()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = code.kernel_launches - launches0
-    code.count_errors(d_out, d_truth, None, d_nerr)
+    flagged = code.last_flagged if mode == "strict" else 0
+    code.count_errors(d_out, d_truth, d_berr, None)
     torch.cuda.synchronize(dev)
+
+    # ---- the other arithmetic mode, for the record (same batch, same timing rules, fewer steps) ----
+    o_steps = max(1, min(args.steps, 3))
+    for _ in range(3):
+        code.decode_device(d_llr, L, out=d_out2, mode=other)
+    barrier()
+    f0, f1 = timed(other, o_steps, d_out2)
+    barrier()
+    ms_other = f0.elapsed_time(f1) / o_steps
+    flagged_other = code.last_flagged if other == "strict" else 0
+    differs_between_modes = int((d_out != d_out2).any(1).sum().item())
+
+    # ---- plain H2D copy of the step's input, all ranks at once (names the end-to-end limiter) ----
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream); d_llr.copy_(h_llr, non_blocking=True); c1.record(stream)
+    barrier()
+    h2d_ms = c0.elapsed_time(c1)
 
     # ---- end-to-end arm: pinned host LLRs in, packed bits out, through the C ABI host entry ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -265,12 +327,22 @@ def run_ours(args):
     barrier()
     e2e_ok = bool(np.array_equal(h_out.numpy(), d_out.cpu().numpy()))
 
-    t = torch.tensor([ms, e2e_s], dtype=torch.float64, device=dev)
-    counts = np.array([[[int(d_nerr.item()), B]]], np.int64)
+    # per-Eb/N0 block-error counters of this rank's shard; global codeword index g uses sweep[g % len(sweep)]
+    ns = len(sweep)
+    be = d_berr.to(torch.int64)
+    counts = np.zeros((1, ns, 2), np.int64)
+    for e in range(ns):
+        off = (e - rank * B) % ns
+        counts[0, e, 0] = int(be[off::ns].sum().item())
+        counts[0, e, 1] = int(be[off::ns].numel())
+    t = torch.tensor([ms, e2e_s, ms_other, h2d_ms], dtype=torch.float64, device=dev)
+    fl = torch.tensor([flagged, flagged_other, differs_between_modes], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(fl, op=dist.ReduceOp.SUM)
         counts = bler.all_reduce_counts(counts, dev)
-    ms, e2e_s = float(t[0].item()), float(t[1].item())
+    ms, e2e_s, ms_other, h2d_ms = (float(x) for x in t.tolist())
+    flagged, flagged_other, differs_between_modes = (int(x) for x in fl.tolist())
 
     if rank == 0:
         ms_step = ms / args.steps
@@ -280,38 +352,69 @@ def run_ours(args):
         traffic, traffic_src = recorded_traffic(args.config, B)
         sm_count = code.info(1)
         achieved = B * bytes_cw / (ms_step * 1e-3) / 1e9     # per GPU: one launch decodes this rank's B codewords
+        strict_flagged = flagged if mode == "strict" else flagged_other
         out = {
             "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": "f32" if mode == "fp32" else ("f64" if mode == "f64" else "f32+f64"),
+            "data": "synthetic",
             "config": {"workload": workload_name(args.config, B), "global_batch": world * B,
-                       "l2": "input %d MiB per GPU per step > 126 MB L2, no flush needed" % (B * N * 4 >> 20),
+                       "arithmetic": {"strict": "fp32 kernels; codewords decided on a margin below tau decoded again in double "
+                                                "(bit-exact against the double reference, see `parity`)",
+                                      "fp32": "fp32 kernels alone", "f64": "everything in double"}[mode],
+                       "l2": "input %d MiB per GPU per step > 126 MB L2, no flush needed" % (B * N * 4 >> 20)
+                             if B * N * 4 > 126e6 else "input %d MiB per GPU per step fits L2 (small plumbing config)" % (B * N * 4 >> 20),
                        "sharding": "contiguous codeword blocks per rank, no data-path collective; counters all-reduced"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "bytes_per_codeword": bytes_cw,
                          "algorithmic_bytes_per_launch": B * bytes_cw,
                          "traffic_source": (traffic_src or {}).get("source"),
+                         "traffic_note": "dram bytes/codeword of the committed ncu --set full capture (batch %s) x this batch"
+                                         % (traffic_src or {}).get("captured_batch", "16384"),
                          "kernel": "scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel",
                          "kernel_kind": code.info(6), "kernel_ms": ms_step},
+            "modes": {mode: value, other: world * B / (ms_other * 1e-3), "unit": "codewords/s (device-resident)",
+                      "strict_flagged_per_step": strict_flagged, "strict_flag_rate": strict_flagged / float(world * B),
+                      "codewords_differing_between_modes": differs_between_modes},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "codewords/s", "h2d_bytes_per_step": B * N * 4,
                     "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok,
-                    "pipelined_chunks": code.info(7)},
+                    "pipelined_chunks": code.info(7), "mode": mode,
+                    "h2d_copy_gbs_per_gpu_all_ranks_at_once": B * N * 4 / (h2d_ms * 1e-3) / 1e9,
+                    "h2d_needed_gbs_per_gpu_at_device_rate": B * N * 4 / (ms_step * 1e-3) / 1e9},
             "gpu_launches": int(launches),
             # informational, beside the contract's HBM roofline: the decoder is bound by instruction issue, so the same
             # rate is also stated against the issue-slot ceiling (148 SMs x 4 schedulers x SM clock), with the warp
             # instructions per codeword taken from the committed ncu capture (profiles/ncu_traffic.json)
             "issue_roofline": issue_roofline(traffic_src, value / world, sm_count, clocks),
             "clocks": clocks,
-            "bler": float(counts[0, 0, 0] / counts[0, 0, 1]),
         }
+        per_point = [{"ebno_db": float(sweep[e]), "n": int(counts[0, e, 1]), "err_gpu": int(counts[0, e, 0]),
+                      "bler_gpu": float(counts[0, e, 0] / counts[0, e, 1]), "ci95": wilson(int(counts[0, e, 0]), int(counts[0, e, 1]))}
+                     for e in range(ns)]
+        out["bler"] = float(counts[0, :, 0].sum() / counts[0, :, 1].sum())
         if world == 1 and not args.no_cpu:
             kind, dec = cpu_decoder(n, K, crc)
             threads = os.cpu_count() or 1
-            v, S = time_cpu(dec, h_llr.numpy(), L, threads, args.cpu_seconds)
+            v, S, want = time_cpu(dec, h_llr.numpy(), L, threads, args.cpu_seconds, want_out=True)
             out["cpu_baseline"] = {
                 "value": v, "unit": "codewords/s", "cores": threads, "kind": kind,
                 "sample": "first %d codewords of the same batch, %s, g++ -O2, one decoder object per thread" % (
-                    S, "unmodified PolarC/PolarCode.cpp (oracle/_ref)" if kind == "reference" else "oracle port")}
+                    S, "unmodified PolarC/PolarCode.cpp (oracle/_ref)" if kind == "reference" else "oracle port"),
+                "table": cpu_table(dec, cpu_decoder_o3(n, K, crc) if kind == "reference" else None, h_llr.numpy(), L, threads,
+                                   min(4.0, args.cpu_seconds))}
+            # parity: the bits the CPU reference just decoded against the GPU's bits for the same codewords
+            got = unpack_bits(d_out[:S].cpu().numpy().view(np.uint32), K)
+            got_other = unpack_bits(d_out2[:S].cpu().numpy().view(np.uint32), K)
+            mm, mmo = (got != want).any(1), (got_other != want).any(1)
+            err_ref, err_gpu = (want != info[:S]).any(1), (got != info[:S]).any(1)
+            out["parity"] = {"against": kind, "compared": int(S), "mismatches": int(mm.sum()), "mode": mode,
+                             "mismatches_that_are_block_errors_in_both": int((mm & err_ref & err_gpu).sum()),
+                             "mismatches_in_%s_mode" % other: int(mmo.sum())}
+            for e in range(ns):
+                sel = (np.arange(S) % ns) == e
+                per_point[e].update({"n_ref_sample": int(sel.sum()), "err_ref_sample": int(err_ref[sel].sum()),
+                                     "err_gpu_same_sample": int(err_gpu[sel].sum())})
+        out["bler_per_ebno"] = per_point
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -324,13 +427,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
-    ap.add_argument("--batch", type=int, default=65536, help="codewords per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="codewords per GPU per step (default 65536; 4096 for c1)")
+    ap.add_argument("--mode", default=os.environ.get("POLAR_B200_MODE", "strict"), choices=["strict", "fp32", "f64"],
+                    help="arithmetic of the headline arm (the other of strict / fp32 is reported in `modes`)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.batch is None:
+        args.batch = 4096 if args.config == "c1" else 65536
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -59,9 +59,13 @@ enum {
  *           codeword whose margin is below tau (polar_b200_set_strict_tau) is decoded again in double. Block lengths /
  *           lists without a margin-reporting kernel run entirely in double. This is what the drop-in class uses.
  *   F64     everything in double with the reference's literal formulas (PolarCode.cpp:438-446, 483, 505-506).
+ *   MINSUM  opt-in, NOT the reference's arithmetic: min-sum check nodes everywhere (the
+ *           reference's own fallback branch, PolarCode.cpp:442-446) and the hardware-friendly metric update (PM += |LLR|
+ *           when a decision contradicts the LLR's sign). No transcendental functions; BLER is measurably worse (bench.py
+ *           --mode minsum reports the delta). N = 2048 and N = 512, lists 1..32 (POLAR_B200_E_UNSUPPORTED elsewhere).
  */
-enum { POLAR_B200_MODE_FP32 = 0, POLAR_B200_MODE_STRICT = 1, POLAR_B200_MODE_F64 = 2 };
-#define POLAR_B200_DEFAULT_STRICT_TAU 1.0e-4f
+enum { POLAR_B200_MODE_FP32 = 0, POLAR_B200_MODE_STRICT = 1, POLAR_B200_MODE_F64 = 2, POLAR_B200_MODE_MINSUM = 3 };
+#define POLAR_B200_DEFAULT_STRICT_TAU 1.0e-5f
 int polar_b200_abi_version(void);
 
 /* Human-readable text for any value returned by this library. */
@@ -211,8 +215,8 @@ enum {
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
     POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode,
-                                            -2 = wide-list kernel (lists 33..127), -3 = wide-list kernel in f64,
-                                            -4 = probability-domain decoder */
+                                            1000 + i = min-sum build i, -2 = wide-list kernel (lists 33..127),
+                                            -3 = wide-list kernel in f64, -4 = probability-domain decoder */
     POLAR_B200_INFO_HOST_CHUNKS = 7,     /* chunks the last *_host call was pipelined in            */
     POLAR_B200_INFO_LAST_FLAGGED = 8     /* codewords the last STRICT call decoded again in double (waits for it) */
 };

@@ -148,7 +148,10 @@ template <class R>
 struct Decoder {
     const Code& c;
     int L;
-    int minsum_only;
+    int minsum_only;     // 0: the reference's rules. 1: min-sum check nodes everywhere (sensitivity probe). 2: min-sum and
+                         // the hardware-friendly metric update max(x, 0) in place of log(1 + exp(x)) -- the checker of the
+                         // product's opt-in MINSUM mode, NOT the reference's arithmetic
+    R metric_inc(R x) const { return minsum_only >= 2 ? std::max(x, R(0)) : softplus_literal<R>(x); }
     // per path: llr tree (layer lam at offset off[lam], 2^(n-lam) entries), partial sums
     // (layer lam at 2*off[lam], 2 phase slots per entry), decided bits, metric, alive flag.
     std::vector<size_t> off;
@@ -211,7 +214,7 @@ struct Decoder {
         for (int l = 0; l < L; ++l) {
             if (!alive[l]) continue;
             C(l, c.n)[phi & 1] = 0;
-            pm[l] += softplus_literal<R>(-A(l, c.n)[0]);
+            pm[l] += metric_inc(-A(l, c.n)[0]);
             U(l)[phi] = 0;
         }
     }
@@ -236,8 +239,8 @@ struct Decoder {
         for (int l = 0; l < L; ++l) {                                         // :497-519
             if (!alive[l]) continue;
             const R lam = A(l, c.n)[0];
-            fork[2 * l] = -(pm[l] + softplus_literal<R>(-lam));
-            fork[2 * l + 1] = -(pm[l] + softplus_literal<R>(lam));
+            fork[2 * l] = -(pm[l] + metric_inc(-lam));
+            fork[2 * l + 1] = -(pm[l] + metric_inc(lam));
             pool_sorted.push_back(fork[2 * l]);
             pool_sorted.push_back(fork[2 * l + 1]);
             ++n_alive;
@@ -271,16 +274,16 @@ struct Decoder {
                 std::copy(U(l), U(l) + phi, U(lp));
                 U(l)[phi] = 0;
                 U(lp)[phi] = 1;
-                pm[l] += softplus_literal<R>(-lam);
-                pm[lp] += softplus_literal<R>(lam);
+                pm[l] += metric_inc(-lam);
+                pm[lp] += metric_inc(lam);
             } else if (keep[2 * l]) {
                 C(l, c.n)[phi & 1] = 0;
                 U(l)[phi] = 0;
-                pm[l] += softplus_literal<R>(-lam);
+                pm[l] += metric_inc(-lam);
             } else {
                 C(l, c.n)[phi & 1] = 1;
                 U(l)[phi] = 1;
-                pm[l] += softplus_literal<R>(lam);
+                pm[l] += metric_inc(lam);
             }
         }
     }

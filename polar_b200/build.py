@@ -56,6 +56,10 @@ def build(force=False, verbose=False, out_dir=None, extra_flags=()):
             jobs.append(([_nvcc()] + flags + ["-DPOLAR_PART=%d" % k, "-c", dev_src[1], "-o", os.path.join(obj, "fast_part%d.o" % k)],
                          "fast_parts.cu part %d" % k))
         procs = [(subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), name) for cmd, name in jobs]
+        # the opt-in min-sum build of a few variants (its own namespace and table, see fast_parts.cu)
+        jobs.append(([_nvcc()] + flags + ["-DPOLAR_MINSUM=1", "-DPOLAR_FAST_NS=fastms", "-c", dev_src[1], "-o",
+                                          os.path.join(obj, "fast_ms.o")], "fast_parts.cu min-sum build"))
+        procs.append((subprocess.Popen(jobs[-1][0], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True), jobs[-1][1]))
         failed = []
         for pr, name in procs:
             out, _ = pr.communicate()
@@ -66,6 +70,7 @@ def build(force=False, verbose=False, out_dir=None, extra_flags=()):
         if failed:
             raise RuntimeError("nvcc failed for: " + ", ".join(failed))
         objs = [os.path.join(obj, "polar_b200.o")] + [os.path.join(obj, "fast_part%d.o" % k) for k in range(FAST_PARTS)]
+        objs.append(os.path.join(obj, "fast_ms.o"))
         subprocess.check_call([_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", dev_so])
     host_so = os.path.join(lib, "libpolar_host.so")
     host_src = [os.path.join(CSRC, "PolarCode.cpp")]

@@ -36,7 +36,7 @@ def pack_bits(bits):
     return np.packbits(pad, axis=-1, bitorder="little").view(np.uint32).reshape(B, KW)
 
 
-MODES = {"fp32": 0, "strict": 1, "f64": 2}
+MODES = {"fp32": 0, "strict": 1, "f64": 2, "minsum": 3}
 
 
 class PolarCode:

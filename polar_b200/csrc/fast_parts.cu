@@ -2,14 +2,34 @@
 // fast_variants.cuh. Entry i of the concatenated table is variant i (POLAR_B200_FAST_VARIANT, POLAR_B200_INFO_KERNEL_KIND).
 #include "fast_variants.cuh"
 
+#if !POLAR_MINSUM
 #ifndef POLAR_PART
 #error "compile with -DPOLAR_PART=0..3"
+#endif
 #endif
 #define POLAR_CAT2(a, b) a##b
 #define POLAR_CAT(a, b) POLAR_CAT2(a, b)
 
 // (log2 N, virtual top layers, first shared-memory layer, log2 lanes per codeword, warps/block, blocks/SM).
 // pick_fast_variant() takes the first entry matching (n, lanes); POLAR_B200_FAST_VARIANT=<index> overrides.
+#if POLAR_MINSUM
+// opt-in fast arithmetic (min-sum check nodes, hardware-friendly path metric): the BASELINE.json block lengths only
+extern const FastVariant kFastMsPart[] = {
+    POLAR_FAST_TM(11, 3, 5, 5, 16, 1),  // N=2048 lists 17..32
+    POLAR_FAST_TM(11, 3, 5, 4, 4, 4),   // lists 9..16
+    POLAR_FAST_TM(11, 3, 5, 3, 4, 4),   // lists 5..8
+    POLAR_FAST_TM(11, 3, 5, 2, 4, 4),   // lists 3..4
+    POLAR_FAST_TM(11, 3, 5, 1, 4, 4),   // list 2
+    POLAR_FAST_TM(11, 3, 5, 0, 4, 4),   // list 1
+    POLAR_FAST_TM(9, 3, 4, 5, 20, 1),   // N=512 lists 17..32
+    POLAR_FAST_TM(9, 3, 4, 4, 4, 5),
+    POLAR_FAST_TM(9, 3, 4, 3, 4, 5),
+    POLAR_FAST_TM(9, 3, 4, 2, 4, 5),
+    POLAR_FAST_TM(9, 3, 4, 1, 4, 5),
+    POLAR_FAST_TM(9, 3, 4, 0, 4, 5),
+};
+extern const int kFastMsPartN = (int)(sizeof(kFastMsPart) / sizeof(FastVariant));
+#else
 extern const FastVariant POLAR_CAT(kFastPart, POLAR_PART)[] = {
 #if POLAR_PART == 0
     // N=2048: layer 3 in the HBM/L2 scratch, layer 4 in tensor memory, layers 5-6 shared, 7-11 registers; 16 warps/SM
@@ -72,16 +92,12 @@ extern const FastVariant POLAR_CAT(kFastPart, POLAR_PART)[] = {
     POLAR_FAST(8, 3, 3, 2, 4, 4),
     POLAR_FAST(8, 3, 3, 1, 4, 4),
     POLAR_FAST(8, 3, 3, 0, 4, 4),
-    // alternates for plain SC at N=2048 (POLAR_B200_FAST_VARIANT=<index>; untested experiments for the next round):
-    // fewer virtual top layers = fewer recomputed check nodes, more layers in the per-warp scratch
-    POLAR_FAST_TM(11, 2, 5, 0, 4, 4),  // 49: layers 2-3 in the scratch
-    POLAR_FAST_TM(11, 1, 5, 0, 4, 4),  // 50: layers 1-3 in the scratch
-    // N=2048 with every per-path layer on the SM: layer 3 in tensor memory (256 columns per warp), layers 4-6 in shared
-    // memory (28 KB per warp), 8 warps/SM; only the one-word partial-sum layer stays in shared memory
-    POLAR_FAST_TM_SG(11, 3, 4, 5, 2, 8, 1),  // 51: lists 17..32
-    POLAR_FAST_TM_SG(11, 3, 4, 2, 2, 8, 1),  // 52: lists 3..4
-    POLAR_FAST_TM_SG(11, 3, 4, 0, 2, 8, 1),  // 53: list 1
-    POLAR_FAST_TM_SG(11, 3, 4, 1, 2, 8, 1),  // 54: list 2
+    // lists 1 and 2 at N=2048 with every per-path layer on the SM: layer 3 in tensor memory (256 columns per warp), layers
+    // 4-6 in shared memory (28 KB per warp), 8 warps/SM (measured +12.6 % on list 1; the same placement lost 32 % at list 32
+    // and changed nothing at list 4, profiles/r02_ab_round1_experiments.txt)
+    POLAR_FAST_TM_SG(11, 3, 4, 0, 2, 8, 1),  // 49: list 1
+    POLAR_FAST_TM_SG(11, 3, 4, 1, 2, 8, 1),  // 50: list 2
 #endif
 };
 extern const int POLAR_CAT(kFastPartN, POLAR_PART) = (int)(sizeof(POLAR_CAT(kFastPart, POLAR_PART)) / sizeof(FastVariant));
+#endif  // POLAR_MINSUM

@@ -46,6 +46,7 @@
 #include "polar_dev.cuh"
 #include "fast_variants.cuh"
 #include "scl_wide.cuh"
+#include "scl_exact.cuh"
 
 namespace {
 
@@ -347,6 +348,17 @@ __global__ void count_errors_kernel(const uint32_t* dec, const uint32_t* truth, 
     if (n_err && (threadIdx.x & 31) == 0 && m) atomicAdd(n_err, (unsigned long long)__popc(m));
 }
 
+// block errors per Eb/N0 point (codeword with global index g belongs to point g % n_ebno); `skip` lists codewords that
+// are counted elsewhere (strict mode's second pass counts the ones it decodes again)
+__global__ void count_errors_bucket_kernel(const uint32_t* dec, const uint32_t* truth, int B, int KW, long long first_index,
+                                           int n_ebno, unsigned long long* err) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    bool e = false;
+    for (int w = 0; w < KW; ++w) e |= dec[(size_t)b * KW + w] != truth[(size_t)b * KW + w];
+    if (e) atomicAdd(err + (int)((unsigned long long)(first_index + b) % (unsigned)n_ebno), 1ull);
+}
+
 // ---- synthetic front end: info bits -> reference encoder -> BPSK/AWGN -> fp32 LLRs, one warp per codeword ----
 // Replaces the per-run generation of the reference's BLER loop (PolarCode.cpp:703-716 info bits + noise,
 // :60-91 encoder, :744-753 channel and LLR) with a counter-based generator: Philox4x32-10 keyed by the seed,
@@ -368,7 +380,7 @@ struct SynthArgs {
     uint32_t* truth;                // [B][KW]
     const uint16_t* inv_order;      // [N]: info index j (< K), K + r for parity bit r, 0xFFFF for frozen positions
     const uint32_t* crc_rows;       // [crc][KW]: parity matrix rows packed over the info index
-    const float* amp;               // [n_ebno]: a = 10^(EbN0/20) sqrt(K/N)   (PolarCode.cpp:744-745)
+    const double* amp;              // [n_ebno]: a = 10^(EbN0/20) sqrt(K/N)   (PolarCode.cpp:744-745)
     unsigned long long seed;
     long long first_index;
     int B, n, K, crc, n_ebno;
@@ -443,30 +455,28 @@ __global__ void __launch_bounds__(128) synth_kernel(const SynthArgs a) {
                 if ((w & sw) == 0) u[w] ^= u[w + sw];
             __syncwarp();
         }
-        // coded[i] = x[bitrev(i)] (PolarCode.cpp:85-87), BPSK 0 -> -1, r = a s + sqrt(1/2) z, llr = -4 r a (:747,:752)
-        const float amp = a.amp[(int)(gidx % (unsigned long long)a.n_ebno)];
+        // coded[i] = x[bitrev(i)] (PolarCode.cpp:85-87), BPSK 0 -> -1, r = a s + sqrt(1/2) z, llr = -4 r a (:747,:752),
+        // all in double like the reference and rounded to float once at the end. One Philox
+        // call = two 53-bit uniforms = one Box-Muller pair; the tails reach |z| = 8.5 (u1 >= 2^-54).
+        const double amp = a.amp[(int)(gidx % (unsigned long long)a.n_ebno)];
         float* out = a.llr + (size_t)b * N;
-        for (int i4 = lane; i4 * 4 < N; i4 += 32) {
+        for (int i2 = lane; i2 * 2 < N; i2 += 32) {
             uint32_t r[4];
-            philox4x32_10(g0, g1, (uint32_t)i4, 1u, k0, k1, r);       // draw index space 1: noise
-            float z[4];
+            philox4x32_10(g0, g1, (uint32_t)i2, 1u, k0, k1, r);       // draw index space 1: noise
+            const double u1 = ((double)(((unsigned long long)r[0] << 21) | (r[1] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+            const double u2 = ((double)(((unsigned long long)r[2] << 21) | (r[3] >> 11)) + 0.5) * (1.0 / 9007199254740992.0);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            const double z[2] = {rad * cs, rad * sn};
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const float u1 = ((float)(r[2 * h] >> 8) + 0.5f) * (1.0f / 16777216.0f);      // (0, 1)
-                const float u2 = ((float)(r[2 * h + 1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-                const float rad = sqrtf(-2.0f * __logf(u1));
-                float sn, cs;
-                __sincosf(6.283185307179586f * u2, &sn, &cs);
-                z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int i = i4 * 4 + q;
+            for (int q = 0; q < 2; ++q) {
+                const int i = i2 * 2 + q;
                 if (i < N) {
                     const unsigned p = a.n ? (__brev((unsigned)i) >> (32 - a.n)) : 0u;
-                    const float c = (float)((u[p >> 5] >> (p & 31)) & 1u);
-                    const float rx = amp * (2.0f * c - 1.0f) + 0.70710678118654752f * z[q];
-                    out[i] = -4.0f * rx * amp;
+                    const double c = (double)((u[p >> 5] >> (p & 31)) & 1u);
+                    const double rx = amp * (2.0 * c - 1.0) + 0.70710678118654752440 * z[q];
+                    out[i] = (float)(-4.0 * rx * amp);
                 }
             }
         }
@@ -493,7 +503,7 @@ struct polar_b200_ctx {
     uint32_t* d_crc_masks = nullptr;
     uint16_t* d_inv_order = nullptr;       // synth: decoding position -> info / parity index
     uint32_t* d_crc_rows = nullptr;        // synth: parity matrix rows packed over the info index
-    float* d_amp = nullptr;                // synth: per-Eb/N0 amplitudes (up to 64)
+    double* d_amp = nullptr;               // synth: per-Eb/N0 amplitudes (up to 64)
     void* d_gx = nullptr;                  // generic-kernel LLR scratch (float or double rows)
     double* d_llr64_stage = nullptr;       // host entry point of the f64 mode
     double* d_prob_stage = nullptr;        // host entry point of the probability-domain decoder: p0 then p1
@@ -521,6 +531,8 @@ struct polar_b200_ctx {
     int* d_flag_count = nullptr;           // [2]: counter of the current call, copy kept for polar_b200_get_info
     int flag_cap = 0;
     float strict_tau = 0.0f;
+    double* d_ex_gx = nullptr;             // scratch of the block-per-codeword double decoder (scl_exact.cuh), grow-only
+    size_t ex_gx_bytes = 0;
     double* d_cvt = nullptr;               // float -> double conversion buffer of the kernels that take one input type
     size_t cvt_bytes = 0;
     long long last_flagged = -1;           // resolved lazily (device counter)
@@ -546,6 +558,14 @@ namespace {
         cudaError_t e__ = (expr);                     \
         if (e__ != cudaSuccess) return (int)e__;      \
     } while (0)
+
+// fused block-error counting (fastcommon::Args / exact::Args): null truth = off
+struct CountSpec {
+    const uint32_t* truth = nullptr;
+    unsigned long long* err = nullptr;
+    long long first_index = 0;
+    int n_ebno = 1;
+};
 
 struct LaunchPlan {
     int wpb, blocks, lamS, smem_x_rows, smem_s_rows, smem_bytes;
@@ -784,11 +804,13 @@ int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_
     return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
-// margin (device, [>= cw_base + B], may be null) / flags: see fast::Args. cw_base = index of llr's first row in the caller's
+// margin (device, [>= cw_base + B], may be null) / flags: see fastcommon::Args. cw_base = index of llr's first row in the caller's
 // batch (the host entry point decodes chunk by chunk but keeps one flag list).
+// variant >= 0: entry of the reference-arithmetic table; variant <= -100: entry -100 - variant of the min-sum table.
 int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st,
-                float* margin = nullptr, int* flag_list = nullptr, int* flag_count = nullptr, float tau = 0.0f, int cw_base = 0) {
-    const FastVariant& v = kFastVariants[variant];
+                float* margin = nullptr, int* flag_list = nullptr, int* flag_count = nullptr, float tau = 0.0f, int cw_base = 0,
+                const CountSpec* cs = nullptr) {
+    const FastVariant& v = variant <= -100 ? kFastMsPart[-100 - variant] : kFastVariants[variant];
     int blocks = c->sm_count * v.bps;
     const int warps = blocks * v.wpb;
     const size_t need_gx = v.gx_floats * warps * sizeof(float), need_gs = v.gs_words * warps * sizeof(uint32_t);
@@ -827,10 +849,20 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
             cudaGetLastError();
         }
     }
-    fast::Args a;
+    fastcommon::Args a;
     a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = c->d_fgx; a.gs = c->d_fgs; a.B = B; a.K = c->K; a.crc = c->crc; a.L = L;
-    a.margin = margin; a.flag_list = flag_list; a.flag_count = flag_count; a.tau = tau; a.cw_base = cw_base;
+    a.margin = margin; a.flag_list = flag_list; a.flag_count = flag_count; a.cw_base = cw_base;
+    a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
+    a.first_index = cs ? cs->first_index : 0; a.n_ebno = cs ? cs->n_ebno : 1;
+    {
+        // thresholds in the kernels' fixed point (Q8.24). With a margin buffer every gap is recorded (calibration);
+        // otherwise only those that will flag the codeword.
+        const double q = (double)tau * 16777216.0;
+        a.tauq_flag = flag_list ? (q >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)q) : 0u;
+        a.tauq = margin ? 0xFFFFFFFFu : a.tauq_flag;
+        a.tau = margin ? INFINITY : (flag_list ? tau : 0.0f);
+    }
     {
         // leading frozen leaves handled by the cooperative phase (whole 16-leaf blocks below layer T's first node)
         const int mt = (1 << v.nlog) >> v.T;
@@ -856,7 +888,8 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     CU_TRY(v.launch(a, blocks, st, attr, nattr));
     CU_TRY(cudaGetLastError());
     c->launches += 1;
-    c->last_wpb = v.wpb; c->last_blocks = blocks; c->last_smem = v.smem_per_warp * v.wpb; c->last_kernel = 1 + variant;
+    c->last_wpb = v.wpb; c->last_blocks = blocks; c->last_smem = v.smem_per_warp * v.wpb;
+    c->last_kernel = variant <= -100 ? 1000 + (-100 - variant) : 1 + variant;
     return POLAR_B200_OK;
 }
 
@@ -897,6 +930,67 @@ int ensure_flags(polar_b200_ctx* c, int B) {
     return 0;
 }
 
+// ---- one block per codeword, double precision (scl_exact.cuh): STRICT mode's re-decode of the flagged codewords ----
+constexpr int kMaxNExact = 13;
+template <class In>
+int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, cudaStream_t st,
+                 const int* list = nullptr, const int* count = nullptr, const CountSpec* cs = nullptr) {
+    const int n = c->n, N = c->N;
+    exact::Args<In> a;
+    memset(&a, 0, sizeof(a));
+    int bps = env_int("POLAR_B200_EXACT_BPS", 1);
+    if (bps < 1) bps = 1;
+    if (bps > 4) bps = 4;
+    const int budget = (220 * 1024) / bps;
+    int off = 0;
+    for (int lam = 0; lam <= n - 1; ++lam) { a.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
+    a.smem_s_rows = off;
+    const int fixed = a.smem_s_rows * 128 + 2 * 16 * 32 + 32 + 16;
+    int lamS = n;                                    // smallest footprint, then grow while it fits
+    while (lamS > 1) {
+        const int xr = (1 << (n - (lamS - 1) + 1)) - 2;
+        if (xr * 256 + fixed > budget) break;
+        --lamS;
+    }
+    a.lamS = lamS;
+    a.smem_x_rows = (1 << (n - lamS + 1)) - 2;
+    const int smem = a.smem_x_rows * 256 + fixed;
+    if (smem > 227 * 1024) return POLAR_B200_E_UNSUPPORTED;
+    const size_t gx_rows = (size_t)N - ((size_t)1 << (n - lamS + 1));
+    a.gx_stride = (gx_rows ? gx_rows : 1) * 32;
+    int blocks = c->sm_count * bps;
+    if (!list && blocks > B) blocks = B;
+    const size_t need = a.gx_stride * (size_t)(c->sm_count * bps) * sizeof(double);
+    if (need > c->ex_gx_bytes) {
+        if (c->d_ex_gx) cudaFree(c->d_ex_gx);
+        c->d_ex_gx = nullptr; c->ex_gx_bytes = 0;
+        CU_TRY(cudaMalloc(&c->d_ex_gx, need));
+        c->ex_gx_bytes = need;
+    }
+    a.llr = llr; a.out = out; a.list = list; a.count = count;
+    a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.gx = c->d_ex_gx;
+    a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
+    a.first_index = cs ? cs->first_index : 0; a.n_ebno = cs ? cs->n_ebno : 1;
+    a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
+    int W = 1; while (W < L) W <<= 1;
+    a.W = W;
+    CU_TRY(cudaFuncSetAttribute(exact::scl_exact_kernel<In>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    exact::scl_exact_kernel<In><<<blocks, exact::NT, smem, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    if (!list) { c->last_wpb = exact::NT / 32; c->last_blocks = blocks; c->last_smem = smem; c->last_kernel = -5; }
+    return POLAR_B200_OK;
+}
+
+// STRICT mode's second pass over the flagged codewords
+int redecode_flagged(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, cudaStream_t st,
+                     const CountSpec* cs = nullptr) {
+    if (c->n <= kMaxNExact && L <= 32 && (cs || env_int("POLAR_B200_REDECODE_GENERIC", 0) == 0))
+        return decode_exact<float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count, cs);
+    return decode_generic<double, float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count);
+}
+
 __global__ void to_double_kernel(const float* in, double* out, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
 }
@@ -916,6 +1010,7 @@ int decode_f64_from_float(polar_b200_ctx* c, const float* llr, int B, int L, uin
         c->launches += 1;
         return decode_wide<double>(c, c->d_cvt, B, L, out, st);
     }
+    if (env_int("POLAR_B200_F64_EXACT_KERNEL", 0) && c->n <= kMaxNExact) return decode_exact<float>(c, llr, B, L, out, st);
     return decode_generic<double, float>(c, llr, B, L, out, st);
 }
 
@@ -928,26 +1023,44 @@ float strict_tau(const polar_b200_ctx* c) {
 // Device-resident decode in one of the three arithmetic modes (include/polar_b200.h). llr / out: device pointers.
 // cw_base / zero_count / redecode serve the chunked host entry point: chunks share one flag list and are re-decoded
 // together after the last chunk.
+// cs: count block errors against cs->truth (fused into the kernels' tails where they support it, a separate small kernel
+// otherwise; `out` must then be a real buffer).
 int decode_mode(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, int mode, float* margin, cudaStream_t st,
-                int fv_forced = -2, int cw_base = 0, bool zero_count = true, bool redecode = true) {
+                int fv_forced = -2, int cw_base = 0, bool zero_count = true, bool redecode = true, const CountSpec* cs = nullptr) {
+    auto count_after = [&](int rc) {
+        if (rc || !cs) return rc;
+        count_errors_bucket_kernel<<<(B + 255) / 256, 256, 0, st>>>(out, cs->truth, B, c->KW, cs->first_index, cs->n_ebno, cs->err);
+        c->launches += 1;
+        return (int)cudaGetLastError();
+    };
     // the fast kernels read the channel rows with 16-byte loads; anything else goes to the generic kernel (scalar loads)
     const bool aligned = (reinterpret_cast<uintptr_t>(llr) & 15u) == 0;
     const int fv = !aligned ? -1 : (fv_forced >= -1 ? fv_forced : pick_fast_variant(c, L, B));
+    if (mode == POLAR_B200_MODE_MINSUM) {
+        // opt-in non-parity arithmetic: only where a min-sum build of a fast kernel exists
+        if (!aligned || L > 32) return POLAR_B200_E_UNSUPPORTED;
+        int wlog = 0;
+        while ((1 << wlog) < L) ++wlog;
+        for (int i = 0; i < kFastMsPartN; ++i)
+            if (kFastMsPart[i].nlog == c->n && kFastMsPart[i].wlog == wlog)
+                return decode_fast(c, -100 - i, llr, B, L, out, st, margin, nullptr, nullptr, 0.0f, 0, cs);
+        return POLAR_B200_E_UNSUPPORTED;
+    }
     if (margin && fv < 0) return POLAR_B200_E_UNSUPPORTED;       // margins are reported by the fast kernels only
     if (mode == POLAR_B200_MODE_FP32) {
-        if (fv >= 0) return decode_fast(c, fv, llr, B, L, out, st, margin);
-        return decode_any<float>(c, llr, B, L, out, st);
+        if (fv >= 0) return decode_fast(c, fv, llr, B, L, out, st, margin, nullptr, nullptr, 0.0f, 0, cs);
+        return count_after(decode_any<float>(c, llr, B, L, out, st));
     }
-    if (mode == POLAR_B200_MODE_F64 || fv < 0) return decode_f64_from_float(c, llr, B, L, out, st);
+    if (mode == POLAR_B200_MODE_F64 || fv < 0) return count_after(decode_f64_from_float(c, llr, B, L, out, st));
     // strict: fp32 everywhere, double where a decision was closer than tau
     int rc = ensure_flags(c, cw_base + B);
     if (rc) return rc;
     if (zero_count) CU_TRY(cudaMemsetAsync(c->d_flag_count, 0, sizeof(int), st));
-    rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, strict_tau(c), cw_base);
+    rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, strict_tau(c), cw_base, cs);
     if (rc) return rc;
     c->flagged_pending = true;
     if (!redecode) return POLAR_B200_OK;
-    return decode_generic<double, float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count);
+    return redecode_flagged(c, llr, B, L, out, st, cs);
 }
 
 // Host memory in and out: the batch is cut into chunks whose H2D copy, decode and D2H copy overlap on three internal
@@ -968,6 +1081,15 @@ int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32
     if (rc) return rc;
     c->have_last = false;                           // this call ends with everything synchronised
     const bool strict = mode == POLAR_B200_MODE_STRICT;
+    if (mode == POLAR_B200_MODE_MINSUM) {
+        CU_TRY(cudaMemcpyAsync(c->d_llr_stage, llr_host, (size_t)B * c->N * sizeof(float), cudaMemcpyHostToDevice, c->st_run));
+        rc = decode_mode(c, c->d_llr_stage, B, L, c->d_out_stage, mode, nullptr, c->st_run);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
+        CU_TRY(cudaStreamSynchronize(c->st_run));
+        c->last_chunks = 1;
+        return POLAR_B200_OK;
+    }
     int fv = pick_fast_variant(c, L, B);
     if (mode == POLAR_B200_MODE_F64 || fv < 0 && (strict || L > 32 || c->n > kMaxNWarp || env_int("POLAR_B200_FORCE_WIDE", 0))) {
         // double everywhere, wide lists, N > 8192: a single chunk on the run stream
@@ -1052,7 +1174,7 @@ int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32
                                cudaMemcpyDeviceToHost, c->st_d2h));
     }
     if (final_copy) {
-        rc = decode_generic<double, float>(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run, c->d_flag_list, c->d_flag_count);
+        rc = redecode_flagged(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
         CU_TRY(cudaStreamSynchronize(c->st_run));
@@ -1145,7 +1267,7 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
                 if (crc_matrix[(size_t)r * K + j] & 1) rows[(size_t)r * c->KW + (j >> 5)] |= 1u << (j & 31);
         if ((rc = (int)cudaMalloc(&c->d_inv_order, (size_t)N * 2)) != 0) return fail(rc);
         if ((rc = (int)cudaMalloc(&c->d_crc_rows, rows.size() * 4)) != 0) return fail(rc);
-        if ((rc = (int)cudaMalloc(&c->d_amp, 64 * sizeof(float))) != 0) return fail(rc);
+        if ((rc = (int)cudaMalloc(&c->d_amp, 64 * sizeof(double))) != 0) return fail(rc);
         if ((rc = (int)cudaMemcpy(c->d_inv_order, inv.data(), (size_t)N * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
         if ((rc = (int)cudaMemcpy(c->d_crc_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
     }
@@ -1162,7 +1284,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_inv_order); cudaFree(c->d_crc_rows); cudaFree(c->d_amp);
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
-    cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt);
+    cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt); cudaFree(c->d_ex_gx);
     cudaFreeHost(c->h_f32); cudaFreeHost(c->h_list); cudaFreeHost(c->h_gather); cudaFreeHost(c->h_out2);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->st_h2d) {
@@ -1181,7 +1303,7 @@ int polar_b200_decode_scl_llr(polar_b200_ctx* c, const float* llr, int B, int L,
 int polar_b200_decode_scl_llr_ex(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* info_packed,
                                  int mode, float* margin, void* cuda_stream) {
     if (!c || !llr || !info_packed || B < 0) return POLAR_B200_E_ARG;
-    if (mode != POLAR_B200_MODE_FP32 && mode != POLAR_B200_MODE_STRICT && mode != POLAR_B200_MODE_F64) return POLAR_B200_E_ARG;
+    if (mode < POLAR_B200_MODE_FP32 || mode > POLAR_B200_MODE_MINSUM) return POLAR_B200_E_ARG;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
@@ -1201,7 +1323,7 @@ int polar_b200_decode_scl_llr_host(polar_b200_ctx* c, const float* llr_host, int
 int polar_b200_decode_scl_llr_host_ex(polar_b200_ctx* c, const float* llr_host, int B, int L,
                                       uint32_t* info_packed_host, int mode, void* cuda_stream) {
     if (!c || !llr_host || !info_packed_host || B < 0) return POLAR_B200_E_ARG;
-    if (mode != POLAR_B200_MODE_FP32 && mode != POLAR_B200_MODE_STRICT && mode != POLAR_B200_MODE_F64) return POLAR_B200_E_ARG;
+    if (mode < POLAR_B200_MODE_FP32 || mode > POLAR_B200_MODE_MINSUM) return POLAR_B200_E_ARG;
     if (L < 1 || L > c->max_list || L > kMaxList) return POLAR_B200_E_LIST;
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
@@ -1358,10 +1480,10 @@ int polar_b200_synthesize(polar_b200_ctx* c, unsigned long long seed, long long 
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    float amp[64];
+    double amp[64];
     for (int i = 0; i < n_ebno; ++i)      // PolarCode.cpp:744-745
-        amp[i] = (float)(pow(10.0, ebno_db[i] / 20.0) * sqrt((double)c->K / (double)c->N));
-    CU_TRY(cudaMemcpyAsync(c->d_amp, amp, n_ebno * sizeof(float), cudaMemcpyHostToDevice, st));
+        amp[i] = pow(10.0, ebno_db[i] / 20.0) * sqrt((double)c->K / (double)c->N);
+    CU_TRY(cudaMemcpyAsync(c->d_amp, amp, n_ebno * sizeof(double), cudaMemcpyHostToDevice, st));
     CU_TRY(cudaStreamSynchronize(st));    // amp[] is a stack buffer
     SynthArgs a;
     a.llr = llr; a.truth = truth_packed; a.inv_order = c->d_inv_order; a.crc_rows = c->d_crc_rows; a.amp = c->d_amp;

@@ -1,0 +1,323 @@
+// scl_exact.cuh -- the latency-oriented double-precision decoder behind STRICT mode: one thread BLOCK per codeword.
+//
+// STRICT mode decodes everything with the fp32 kernels and then decodes again, in the reference's own arithmetic
+// (double, literal formulas, PolarC/PolarCode.cpp:438-446, 483, 505-506), the few codewords that took a decision on a
+// margin the fp32 arithmetic cannot vouch for. There are only a few hundred of those per batch, so what matters is
+// how long ONE double-precision decode takes, not how many run side by side: the warp-per-codeword generic kernel
+// (polar_b200.cu) needs 10+ ms for one codeword regardless of how empty the GPU is.
+//
+// Same organisation as the generic kernel (path-interleaved rows [beta][32], 5-bit column pointers instead of lazy
+// copies, packed partial sums, butterfly order, u-hat by polar transform -- see polar_b200.cu), with two changes:
+//   * the refresh of a tree layer (PolarCode.cpp:422-455) is spread over all threads of the block, work item =
+//     (path, beta), whenever the layer has more than 32 items; the small layers at the bottom of the tree, the leaf
+//     decision (PolarCode.cpp:475-607) and the partial-sum chain (:457-473) are done by warp 0 alone, lane = list path.
+//     Block barriers are needed only around the big layers; runs of leaves that touch small layers only are decoded by
+//     warp 0 without any block-wide synchronisation;
+//   * column pointers and the active mask live in shared memory (every warp needs them), the rest of the per-path state
+//     in warp 0's registers.
+// Every rule of order is the reference's, exactly as in the other kernels: fork selection = the rho best forks under
+// (metric, fork index) (:528-553), kills pushed / clones popped in ascending path order (:555-570, :274-303), first
+// path = L-1 (:250-263), final pick = strictly smaller metric, lowest index, parity filter with fall-through (:609-644).
+//
+// Included by polar_b200.cu after polar_dev.cuh.
+#pragma once
+
+namespace exact {
+
+constexpr int NT = 256;          // threads per block
+
+template <class In>
+struct Args {
+    const In* llr;               // [B][N], converted to double on load
+    uint32_t* out;               // [B][KW]
+    const int* list;             // null, or the codeword indices to decode
+    const int* count;            // with `list`: number of entries (device memory)
+    const uint32_t* frozen_words;
+    const uint16_t* info_order;
+    const uint32_t* crc_masks;
+    double* gx;                  // per-block scratch rows (32 doubles each) of layers 1 .. lamS-1
+    unsigned long long gx_stride;// doubles per block
+    int B, n, K, crc, L;
+    int W;                       // list size rounded up to a power of two (work is spread over W paths x beta)
+    int lamS;                    // first layer kept in shared memory
+    int smem_x_rows, smem_s_rows;
+    int s_off[kMaxN + 2];        // word-row offset of partial-sum layer lam (all of them in shared memory)
+    // fused block-error counting, as in fast::Args
+    const uint32_t* truth;
+    unsigned long long* err;
+    long long first_index;
+    int n_ebno;
+};
+
+template <class In>
+__global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int n = a.n, N = 1 << n, L = a.L, W = a.W, lamS = a.lamS;
+    int wsh = 0;
+    while ((1 << wsh) < W) ++wsh;
+    const int NW = (N + 31) >> 5, KW = (a.K + 31) >> 5;
+    const int slot = lane;                       // warp 0: lane = list path (lanes >= W never become active)
+    const unsigned gmask_lo = (W == 32) ? FULL_MASK : ((1u << W) - 1u);
+
+    double* sx = reinterpret_cast<double*>(smem_raw);
+    uint32_t* ss = reinterpret_cast<uint32_t*>(sx + (size_t)a.smem_x_rows * 32);
+    unsigned char* px = reinterpret_cast<unsigned char*>(ss + (size_t)a.smem_s_rows * 32);   // [16][32] LLR column pointers
+    unsigned char* ps = px + 16 * 32;                                                        // [16][32] partial-sum pointers
+    unsigned char* srcof = ps + 16 * 32;                                                     // [32] clone scatter
+    volatile uint32_t* actp = reinterpret_cast<volatile uint32_t*>(srcof + 32);              // active-path mask
+    double* gx = a.gx + a.gx_stride * blockIdx.x;
+
+    auto xrow = [&](int lam, int beta) -> double* {
+        if (lam >= lamS) return sx + ((size_t)((1 << (n - lamS + 1)) - (1 << (n - lam + 1)) + beta) << 5);
+        return gx + ((size_t)(N - (1 << (n - lam + 1)) + beta) << 5);
+    };
+    auto srow = [&](int lam, int w) -> uint32_t* { return ss + ((size_t)(a.s_off[lam] + w) << 5); };
+
+    const int nB = a.list ? *a.count : a.B;
+    for (int item = blockIdx.x; item < nB; item += gridDim.x) {
+        const int cw = a.list ? a.list[item] : item;
+        const In* chan = a.llr + (size_t)cw * N;
+
+        // per-path state of warp 0 (PolarCode.cpp:250-263: free stack 0..L-1, first path = L-1)
+        bool active = (wib == 0) && (slot == L - 1);
+        double pm = 0;
+        uint32_t s_n = 0;
+        int stk = slot, sp = L - 1;
+        double lam_n = 0;
+        uint32_t frozen_word = 0;
+        __syncthreads();                                   // the previous codeword's output gather is done
+        for (int i = tid; i < 2 * 16 * 32; i += NT) px[i] = 0;          // px and ps
+        if (tid == 0) *actp = 1u << (L - 1);
+        __syncthreads();
+
+        // one tree layer for every active path: items (path, i), spread over the threads t0, t0 + T, ...
+        auto refresh = [&](int lam, bool is_g, int t0, int T) {
+            const int M = 1 << (n - lam);
+            const int total = M << wsh;
+            const uint32_t act = *actp;
+            for (int idx = t0; idx < total; idx += T) {
+                const int path = idx & (W - 1), i = idx >> wsh;
+                if (!((act >> path) & 1u)) continue;
+                double x0, x1;
+                int beta = i;
+                if (lam == 1) {
+                    // channel layer: reference pairs are (2k, 2k+1); the result lands at the bit-reversed position
+                    x0 = (double)chan[2 * i]; x1 = (double)chan[2 * i + 1];
+                    beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
+                } else {
+                    const double* src = xrow(lam - 1, 0) + px[(lam - 2) * 32 + path];
+                    x0 = src[(size_t)i << 5];
+                    x1 = src[(size_t)(i + M) << 5];
+                }
+                double y;
+                if (is_g) {
+                    uint32_t bit;
+                    if (lam == n) bit = s_n & 1u;                              // small layer: idx == lane == path (warp 0)
+                    else bit = (srow(lam, beta >> 5)[ps[(lam - 1) * 32 + path]] >> (beta & 31)) & 1u;
+                    y = x1 + (bit ? -x0 : x0);                                 // PolarCode.cpp:448-451
+                } else {
+                    y = Arith<double>::f(x0, x1);                              // PolarCode.cpp:438-446
+                }
+                if (lam == n) lam_n = y; else xrow(lam, beta)[path] = y;
+            }
+        };
+
+        for (int phi = 0; phi < N; ++phi) {
+            // ---- refresh LLR layers lam_top..n (PolarCode.cpp:422-455): big layers by the block, small ones by warp 0 ----
+            const int lam_top = (phi == 0) ? 1 : n - (__ffs(phi) - 1);
+            const bool any_big = ((1 << (n - lam_top)) << wsh) > 32;
+            if (any_big) __syncthreads();                  // warp 0's decisions of the leaves before this one are visible
+            for (int lam = lam_top; lam <= n; ++lam) {
+                const bool big = ((1 << (n - lam)) << wsh) > 32;
+                const bool is_g = (lam == lam_top) && (phi != 0);
+                if (big) {
+                    refresh(lam, is_g, tid, NT);
+                    if (lam < n && tid < 32) px[(lam - 1) * 32 + tid] = (unsigned char)tid;
+                    __syncthreads();
+                } else if (wib == 0) {
+                    refresh(lam, is_g, lane, 32);
+                    if (lam < n) px[(lam - 1) * 32 + lane] = (unsigned char)lane;
+                    __syncwarp();
+                }
+            }
+            if (wib != 0) continue;                        // the other warps wait at the next leaf with a big layer
+
+            // ---- leaf decision (warp 0, lane = path) ----
+            if ((phi & 31) == 0) frozen_word = a.frozen_words[phi >> 5];
+            const bool frozen = (frozen_word >> (phi & 31)) & 1u;
+            uint32_t u = 0;
+            if (frozen) {
+                if (active) pm += Arith<double>::softplus(-lam_n);             // PolarCode.cpp:475-487
+            } else {
+                // PolarCode.cpp:489-607. Metrics are kept positive (m = -probForks).
+                const double m0 = pm + Arith<double>::softplus(-lam_n);
+                const double m1 = pm + Arith<double>::softplus(lam_n);
+                const unsigned act_g = __ballot_sync(FULL_MASK, active) & gmask_lo;
+                const int A = __popc(act_g);
+                bool keep0 = active, keep1 = active;
+                bool slow = 2 * A > L;                                         // warp-uniform
+                if (slow && A == L) {
+                    // common case: every likely fork strictly beats every unlikely fork and the list is full
+                    const double lo = rmin<double>(m0, m1), hi = rmax<double>(m0, m1);
+                    const double worst_likely = group_max<double>(active ? lo : -CUDART_INF, 32);
+                    const double best_unlikely = group_min<double>(active ? hi : CUDART_INF, 32);
+                    if (best_unlikely > worst_likely) {
+                        slow = false;
+                        keep0 = active && (m0 <= m1);    // m0 == m1 cannot happen here (would not be strict)
+                        keep1 = active && !keep0;
+                    }
+                }
+                if (slow) {
+                    // exact rule: keep the rho best of the 2A forks under (metric asc, fork index asc)
+                    // == PolarCode.cpp:528-553 (sort, threshold, '>' pass then '==' pass in index order)
+                    int r0 = 0, r1 = 0;
+                    for (int j = 0; j < W; ++j) {
+                        const double o0 = __shfl_sync(FULL_MASK, m0, j);
+                        const double o1 = __shfl_sync(FULL_MASK, m1, j);
+                        if ((act_g >> j) & 1u) {
+                            r0 += (o0 < m0) || (o0 == m0 && j < slot);
+                            r0 += (o1 < m0) || (o1 == m0 && j < slot);
+                            r1 += (o0 < m1) || (o0 == m1 && j <= slot);
+                            r1 += (o1 < m1) || (o1 == m1 && j < slot);
+                        }
+                    }
+                    keep0 = active && r0 < L;
+                    keep1 = active && r1 < L;
+                }
+                const bool kill = active && !keep0 && !keep1;
+                const bool clone = keep0 && keep1;
+                const unsigned Kg = __ballot_sync(FULL_MASK, kill) & gmask_lo;
+                const unsigned Cg = __ballot_sync(FULL_MASK, clone) & gmask_lo;
+                if ((Kg | Cg) == 0) {
+                    if (active) { u = keep1 ? 1u : 0u; pm = keep1 ? m1 : m0; }
+                } else {
+                    const int nk = __popc(Kg), nc = __popc(Cg);
+                    // killPath pushes in ascending path order (PolarCode.cpp:555-560, :292)
+                    if (slot >= sp && slot < sp + nk) stk = (int)__fns(Kg, 0, slot - sp + 1);
+                    const int sp2 = sp + nk;
+                    // clonePath pops for ascending l (PolarCode.cpp:562-570, :275-276)
+                    const int ci = __popc(Cg & ((1u << slot) - 1u));
+                    const int tgt = __shfl_sync(FULL_MASK, stk, (sp2 - 1 - ci) & 31);
+                    sp = sp2 - nc;
+                    srcof[lane] = (unsigned char)lane;
+                    __syncwarp();
+                    if (clone) srcof[tgt] = (unsigned char)lane;
+                    __syncwarp();
+                    const int src_lane = srcof[lane];
+                    __syncwarp();
+                    const bool is_new = (src_lane != lane);
+                    const double src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
+                    const uint32_t src_sn = __shfl_sync(FULL_MASK, s_n, src_lane);
+                    // a clone takes over its parent's column pointers (both tables: 2 x 16 rows of 32 bytes)
+                    unsigned char cp[32];
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) cp[r] = px[r * 32 + src_lane];
+                    __syncwarp();
+                    if (is_new) {
+#pragma unroll
+                        for (int r = 0; r < 32; ++r) px[r * 32 + lane] = cp[r];
+                        active = true; pm = src_m1; u = 1u; s_n = src_sn;
+                    } else if (kill) {
+                        active = false; pm = 0;
+                    } else if (active) {
+                        u = keep0 ? 0u : 1u;
+                        pm = keep0 ? m0 : m1;
+                    }
+                    const unsigned now = __ballot_sync(FULL_MASK, active);
+                    if (lane == 0) *actp = now;
+                }
+            }
+
+            // ---- partial sums (PolarCode.cpp:457-473), bit-packed, butterfly order ----
+            if ((phi & 1) == 0) {
+                s_n = u;
+            } else {
+                const int t = __ffs(~phi) - 1;           // trailing ones of phi, 1..n
+                const int lam_end = n - t;               // layer whose S array receives the result
+                uint32_t P = u;
+                int lam = n;
+                while (lam > lam_end && (n - lam) < 5) {
+                    const int M = 1 << (n - lam);
+                    uint32_t Sw;
+                    if (lam == n) Sw = s_n;
+                    else Sw = srow(lam, 0)[ps[(lam - 1) * 32 + lane]];
+                    P = ((Sw ^ P) & ((1u << M) - 1u)) | (P << M);
+                    --lam;
+                }
+                __syncwarp();       // every lane has read the columns that are about to be overwritten
+                if (lam == lam_end) {
+                    srow(lam, 0)[lane] = P;
+                } else {
+                    const int Wd = 1 << (t - 5);          // words of the destination vector
+                    uint32_t* D = srow(lam_end, 0) + lane;
+                    D[(size_t)(Wd - 1) << 5] = P;
+                    for (; lam > lam_end; --lam) {
+                        const int mw = 1 << (n - lam - 5);
+                        const int base = Wd - mw;
+                        const uint32_t* S = srow(lam, 0) + ps[(lam - 1) * 32 + lane];
+                        for (int w = 0; w < mw; ++w)
+                            D[(size_t)(base - mw + w) << 5] = S[(size_t)w << 5] ^ D[(size_t)(base + w) << 5];
+                    }
+                }
+                if (lam_end >= 1) ps[(lam_end - 1) * 32 + lane] = (unsigned char)lane;
+            }
+            __syncwarp();
+        }
+
+        if (wib == 0) {
+            // ---- u-hat of every path: packed polar transform of the re-encoded codeword (layer 0) ----
+            uint32_t* D = srow(0, 0) + lane;
+            for (int sw = NW >> 1; sw >= 1; sw >>= 1)
+                for (int i = 0; i < NW; ++i)
+                    if ((i & sw) == 0) D[(size_t)i << 5] ^= D[(size_t)(i + sw) << 5];
+            bool pass = true;
+            for (int i = 0; i < NW; ++i) {
+                uint32_t w = D[(size_t)i << 5];
+                if (N > 16) w ^= (w >> 16) & 0x0000FFFFu;
+                if (N > 8) w ^= (w >> 8) & 0x00FF00FFu;
+                if (N > 4) w ^= (w >> 4) & 0x0F0F0F0Fu;
+                if (N > 2) w ^= (w >> 2) & 0x33333333u;
+                w ^= (w >> 1) & 0x55555555u;
+                D[(size_t)i << 5] = w;
+            }
+            for (int r = 0; r < a.crc; ++r) {            // PolarCode.cpp:93-108
+                uint32_t acc = 0;
+                for (int i = 0; i < NW; ++i) acc ^= D[(size_t)i << 5] & a.crc_masks[(size_t)r * NW + i];
+                if (__popc(acc) & 1) pass = false;
+            }
+            // ---- final pick, PolarCode.cpp:609-644 ----
+            const unsigned act_all = __ballot_sync(FULL_MASK, active);
+            const unsigned pass_g = __ballot_sync(FULL_MASK, active && pass);
+            const bool use_parity = (a.crc != 0) && (pass_g != 0);
+            const bool eligible = active && (use_parity ? pass : true) && (pm < CUDART_INF);
+            const double best = group_min<double>(eligible ? pm : CUDART_INF, 32);
+            const unsigned cand = __ballot_sync(FULL_MASK, eligible && pm == best);
+            const int win = cand ? (__ffs(cand) - 1) : 0;
+            const bool wa = (act_all >> win) & 1u;
+            __syncwarp();
+            // ---- output gather: decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174 ----
+            const uint32_t* U = srow(0, 0) + win;
+            bool differs = false;
+            for (int t = lane; t < KW; t += 32) {
+                uint32_t word = 0;
+                if (wa) {
+                    const int jmax = min(32, a.K - 32 * t);
+                    for (int i = 0; i < jmax; ++i) {
+                        const int pos = a.info_order[32 * t + i];
+                        word |= ((U[(size_t)(pos >> 5) << 5] >> (pos & 31)) & 1u) << i;
+                    }
+                }
+                if (a.out != nullptr) a.out[(size_t)cw * KW + t] = word;
+                if (a.truth != nullptr) differs |= word != a.truth[(size_t)cw * KW + t];
+            }
+            if (a.truth != nullptr) {                        // PolarCode.cpp:758-769
+                const bool block_error = __any_sync(FULL_MASK, differs);
+                if (lane == 0 && block_error)
+                    atomicAdd(a.err + (int)((unsigned long long)(a.first_index + cw) % (unsigned)a.n_ebno), 1ull);
+            }
+        }
+    }
+}
+
+}  // namespace exact

@@ -32,7 +32,51 @@
 #pragma once
 #include <type_traits>
 
-namespace fast {
+// POLAR_MINSUM=1 (with POLAR_FAST_NS=fastms) compiles the same kernels in the opt-in, NON-PARITY fast arithmetic of
+// pure min-sum check nodes (the reference's own fallback branch, PolarC/PolarCode.cpp:442-446,
+// applied everywhere) and the hardware-friendly path-metric update of Balatsoukas-Stimming et al. (PM += |LLR| when
+// the decision contradicts the LLR's sign, nothing otherwise) -- no transcendental at all. Checked bit for bit against
+// the oracle's minsum_only = 2 mode, never against the reference.
+#ifndef POLAR_MINSUM
+#define POLAR_MINSUM 0
+#endif
+#ifndef POLAR_FAST_NS
+#define POLAR_FAST_NS fast
+#endif
+
+namespace fastcommon {
+struct Args {
+    const float* llr;
+    uint32_t* out;
+    const uint32_t* frozen_words;
+    const uint16_t* info_order;
+    const uint32_t* crc_masks;
+    float* gx;
+    uint32_t* gs;
+    int B, K, crc, L;
+    int PA;            // leading frozen leaves decoded cooperatively (multiple of 16, < N >> T)
+    // decision margins (strict mode, DESIGN.md section 2): the smallest gap any keep/drop decision of a codeword was
+    // taken with. margin (may be null): [B] floats out. flag_list / flag_count (may be null): codewords whose margin
+    // is below tau are appended (atomic counter) for re-decoding in reference precision.
+    float* margin;
+    int* flag_list;
+    int* flag_count;
+    float tau;         // plain SC: |LLR| below tau is recorded;  lists: gaps below tauq (Q8.24)
+    uint32_t tauq;
+    uint32_t tauq_flag;// codewords whose smallest recorded margin is below this are appended to flag_list
+    int cw_base;       // index of llr's row 0 in the caller's batch (margin / flag_list are indexed by batch position)
+    // block-error counting fused into the tail (the comparison loop of the BLER harness, PolarCode.cpp:758-769):
+    // truth (may be null): [B][KW] packed info bits; err: one counter per Eb/N0 point, codeword with global index g
+    // belongs to point g % n_ebno. Codewords that strict mode flags are counted by the second pass instead.
+    // out may be null when only the counters are wanted.
+    const uint32_t* truth;
+    unsigned long long* err;
+    long long first_index;
+    int n_ebno;
+};
+}  // namespace fastcommon
+
+namespace POLAR_FAST_NS {
 
 // channel LLRs: read-only path. (Streaming / evict-first loads were measured 5% slower: each codeword's
 // LLRs are re-read by four top-layer nodes and those re-reads do hit L2.)
@@ -98,25 +142,7 @@ struct Cfg {
     static constexpr size_t GS_WORDS = (size_t)GS_ROWS * 32;
 };
 
-struct Args {
-    const float* llr;
-    uint32_t* out;
-    const uint32_t* frozen_words;
-    const uint16_t* info_order;
-    const uint32_t* crc_masks;
-    float* gx;
-    uint32_t* gs;
-    int B, K, crc, L;
-    int PA;            // leading frozen leaves decoded cooperatively (multiple of 16, < N >> T)
-    // decision margins (strict mode, DESIGN.md section 2): the smallest gap any keep/drop decision of a codeword was
-    // taken with. margin (may be null): [B] floats out. flag_list / flag_count (may be null): codewords whose margin
-    // is below tau are appended (atomic counter) for re-decoding in reference precision.
-    float* margin;
-    int* flag_list;
-    int* flag_count;
-    float tau;
-    int cw_base;       // index of llr's row 0 in the caller's batch (margin / flag_list are indexed by batch position)
-};
+using fastcommon::Args;
 
 struct Warp {          // per-warp pointers
     float* sx;         // shared LLR rows
@@ -136,7 +162,7 @@ struct Warp {          // per-warp pointers
 };
 
 struct Lane {          // per-path state
-    float pm;
+    uint32_t pm;       // path metric above the list's best, Q8.24 (q_of / q_add)
     bool active;
     unsigned long long px;   // column pointers of LLR layers T.. (index lam - T)
     unsigned long long ps;   // column pointers of partial-sum word layers 1..SWL (index lam - 1)
@@ -181,11 +207,23 @@ template <class P> __device__ __forceinline__ P* shfl_ptr(P* p, int src) {
     return reinterpret_cast<P*>(__shfl_sync(FULL_MASK, reinterpret_cast<unsigned long long>(p), src));
 }
 
+// ---- path metrics in fixed point (Q8.24: 2^-24 ~ 6e-8 resolution, saturating at 256) ----
+// The reference keeps metrics in double; a float metric of magnitude ~700 (every frozen bit adds up to ln 2) resolves
+// only 6e-5, which alone made 4 % of the list-32 codewords tie somewhere. Only metric DIFFERENCES within a codeword
+// decide anything (PolarCode.cpp:528-553, 609-644), so the kernel keeps metric - (smallest metric of the list), renormalised
+// once per 16 leaves, as an unsigned fixed-point number: additions are exact, keys need no conversion for the warp
+// REDUX, and a saturated key (>= 256 above the best path, or the reference's +inf) still orders correctly against any
+// unsaturated one. Two saturated keys compare equal, which shows up as a zero margin.
+constexpr float kQScale = 16777216.0f;
+constexpr uint32_t kQSat = 0xFFFFFFFFu;
+__device__ __forceinline__ uint32_t q_of(float x) { return __float2uint_rn(x * kQScale); }        // x >= 0; saturates
+__device__ __forceinline__ uint32_t q_add(uint32_t a, uint32_t b) { const uint32_t r = a + b; return r < a ? kQSat : r; }
+
 // Decision margin: the gap (>= 0) between the worst fork that was kept and the best fork that was dropped. A gap
 // below the arithmetic's own error means the double-precision reference may decide otherwise; such codewords are
-// re-decoded in double (strict mode). Non-negative floats order like their bit patterns; NaN (inf - inf) sorts last.
-template <int W> __device__ __forceinline__ void note_margin(const Warp& w, float gap) {
-    if ((w.lane & (W - 1)) == 0) atomicMin(w.mg + w.g, __float_as_uint(gap));
+// re-decoded in double (strict mode). Only gaps below tauq are recorded (the smallest one per codeword).
+template <int W> __device__ __forceinline__ void note_gap(const Warp& w, uint32_t gapq, uint32_t tauq) {
+    if (gapq < tauq && (w.lane & (W - 1)) == 0) atomicMin(w.mg + w.g, gapq);
 }
 
 // ---- tensor memory as a per-warp scratch (tcgen05.ld/st, shape 32x32b: lane i of the warp <-> TMEM lane i of
@@ -260,9 +298,6 @@ __device__ __forceinline__ float g_rule(float a, float b, uint32_t bit) {
 #ifndef POLAR_UNROLL2
 #define POLAR_UNROLL2 2
 #endif
-#ifndef POLAR_TOP_PIPE
-#define POLAR_TOP_PIPE 1
-#endif
 #ifndef POLAR_PS_SHORTCUT
 #define POLAR_PS_SHORTCUT 1
 #endif
@@ -273,8 +308,16 @@ __device__ __forceinline__ float sign_min(float a, float b) {
     return __int_as_float(__float_as_int(fminf(fabsf(a), fabsf(b))) |
                           ((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000));
 }
+#if POLAR_MINSUM
+// these hide the reference-rule helpers of polar_dev.cuh inside this namespace
+__device__ __forceinline__ float f_rule(float a, float b) { return sign_min(a, b); }
+__device__ __forceinline__ float softplus_ref(float x) { return fmaxf(x, 0.0f); }
+__device__ __forceinline__ float log1p_exp_neg(float) { return 0.0f; }
+#endif
 __device__ __forceinline__ void f_rule2(float a0, float b0, float a1, float b1, float& y0, float& y1) {
-#if POLAR_PACKED
+#if POLAR_MINSUM
+    y0 = sign_min(a0, b0); y1 = sign_min(a1, b1);
+#elif POLAR_PACKED
     const float2 A = make_float2(a0, a1);
     const float2 S = __fadd2_rn(A, make_float2(b0, b1));
     const float2 D = __fadd2_rn(A, make_float2(-b0, -b1));
@@ -357,39 +400,6 @@ __device__ __forceinline__ void layer_step(const Warp& w, Lane& s) {
                 for (int j = 0; j < 4; ++j) { a[j] = na[j]; b[j] = nb[j]; }
             }
             tm_wait_st();
-            s.px = set_ptr(s.px, LAM - C::T, w.lane);
-            return;
-        }
-#endif
-#if POLAR_TM_PIPE >= 2
-        if constexpr (SRC_TM) {
-            // EXPERIMENT (not the default, untested on hardware): tensor-memory source double-buffered over two explicit
-            // register sets. tcgen05.wait::ld waits for every earlier load, so the order is: load set 1, compute on
-            // set 0 (complete since the previous wait), wait, reload set 0, compute on set 1, wait.
-            static_assert(M % 8 == 0, "two groups of four per iteration");
-            float a0[4], b0[4], a1[4], b1[4];
-            tm_ld4(w.tm, a0); tm_ld4(w.tm + M, b0);
-            tm_wait_ld();
-#pragma unroll 1
-            for (int i0 = 0; i0 < M; i0 += 8) {
-                tm_ld4(w.tm + i0 + 4, a1); tm_ld4(w.tm + i0 + 4 + M, b1);
-                if constexpr (ISG) { if ((i0 & 31) == 0) word = sw[(i0 >> 5) * 32]; }
-                float ca[4], cb[4], y[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { ca[j] = __shfl_sync(FULL_MASK, a0[j], pcol); cb[j] = __shfl_sync(FULL_MASK, b0[j], pcol); }
-                node4<ISG>(ca, cb, word, i0 & 31, y);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[(i0 + j) * 32] = y[j];
-                tm_wait_ld();
-                const int nx = (i0 + 8 < M) ? i0 + 8 : i0;            // last iteration re-reads itself (harmless)
-                tm_ld4(w.tm + nx, a0); tm_ld4(w.tm + nx + M, b0);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) { ca[j] = __shfl_sync(FULL_MASK, a1[j], pcol); cb[j] = __shfl_sync(FULL_MASK, b1[j], pcol); }
-                node4<ISG>(ca, cb, word, (i0 + 4) & 31, y);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dst[(i0 + 4 + j) * 32] = y[j];
-                tm_wait_ld();
-            }
             s.px = set_ptr(s.px, LAM - C::T, w.lane);
             return;
         }
@@ -605,10 +615,6 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
 #if POLAR_SW_PIPE
         load_sw(0, sw);
 #endif
-#if POLAR_TOP_PIPE >= 2
-        float va[2][CNT];
-        top_load_pair<C, NODE, 0>(w, 0, va);
-#endif
 #pragma unroll 1
         for (int wd = 0; wd < MT / 32; ++wd) {
 #if POLAR_SW_PIPE
@@ -638,19 +644,6 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                 if constexpr (DST_TM) { tm_st1(w.tm + beta, v[0][0]); tm_st1(w.tm + beta + 1, v[1][0]); }
                 else { dst[beta * 32] = v[0][0]; dst[(beta + 1) * 32] = v[1][0]; }
             };
-#if POLAR_TOP_PIPE >= 2
-            // EXPERIMENT (not the default, untested on hardware): the one-pair-ahead prefetch also runs across the
-            // 32-beta groups, so only the very first pair of a node is waited for (va is declared outside the loop)
-            float vb[2][CNT];
-#pragma unroll 1
-            for (int bi = 0; bi < 32; bi += 4) {
-                top_load_pair<C, NODE, 1>(w, wd * 32 + bi, vb);
-                compute_pair(bi, va);
-                const int nq = wd * 32 + bi + 4;
-                top_load_pair<C, NODE, 0>(w, nq < MT ? nq : MT - 4, va);         // the last one re-reads (harmless)
-                compute_pair(bi + 2, vb);
-            }
-#else
             float va[2][CNT], vb[2][CNT];
             top_load_pair<C, NODE, 0>(w, wd * 32, va);
 #pragma unroll 1
@@ -660,7 +653,6 @@ __device__ __forceinline__ void top_node(const Warp& w, Lane& s) {
                 top_load_pair<C, NODE, 0>(w, wd * 32 + ((bi + 4) & 31), va);   // wraps harmlessly
                 compute_pair(bi + 2, vb);
             }
-#endif
 #if POLAR_SW_PIPE
             static_for<0, (1 << T)>([&](auto i_c) { sw[decltype(i_c)::value] = swn[decltype(i_c)::value]; });
 #endif
@@ -913,33 +905,37 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
 
 // ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607); W lanes = the list of one codeword ----
 // Returns the decided bit of this lane's (possibly new) path. `permuted` is warp-uniform.
+// tauq / tau: decision gaps below this (fixed point / float for plain SC) are recorded in the warp's margin slots.
 template <class C>
 __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp, bool& permuted,
-                                              int& src_lane) {
+                                              int& src_lane, uint32_t tauq, float tau) {
     constexpr int W = C::W;
     const int lane = w.lane;
     const int gbase = lane & ~(W - 1), slot = lane & (W - 1);
-    // both fork metrics from one log1p(exp(-|x|)) (softplus_ref(-|x|) and softplus_ref(+|x|))
     const float ax = fabsf(lam_n);
-    const float t = log1p_exp_neg(ax);
-    const float mlo = s.pm + ((ax >= 36.7368f) ? 0.0f : t);                       // likely fork
-    const float mhi = s.pm + ((ax >= 709.78271484375f) ? CUDART_INF_F : ax + t);  // unlikely fork
     const bool neg = lam_n < 0.0f;
-    const float m0 = neg ? mhi : mlo, m1 = neg ? mlo : mhi;
-    const unsigned act = gballot<W>(s.active, gbase);
-    const int A = __popc(act);
     permuted = false;
     src_lane = lane;
-    bool keep0 = s.active, keep1 = s.active;
-    // keep the L best forks under (metric asc, fork index asc). Metrics are >= 0: uint order = float order.
-    const unsigned klo = __float_as_uint(mlo), khi = __float_as_uint(mhi);
-    const bool like1 = m1 < m0;                            // likely fork is bit 1
     if constexpr (W == 1) {
-        // plain SC (list 1): the better of the two forks survives, fork 0 on a tie (index order, PolarCode.cpp:543-553)
-        if (s.active) s.pm = like1 ? m1 : m0;
-        note_margin<W>(w, ax);                              // the decision is the sign of the leaf LLR
-        return like1 ? 1u : 0u;
+        // plain SC (list 1): the better of the two forks survives, fork 0 on a tie (index order, PolarCode.cpp:543-553),
+        // i.e. the sign of the leaf LLR; no metric is kept at all (a single path needs none). Margin = |LLR|.
+        if (ax < tau) atomicMin(w.mg + w.g, q_of(ax));
+        return neg ? 1u : 0u;
     }
+    // both fork metrics from one log1p(exp(-|x|)) (softplus_ref(-|x|) and softplus_ref(+|x|)), as fixed-point increments
+    const float t = log1p_exp_neg(ax);
+#if POLAR_MINSUM
+    const uint32_t klo = s.pm, khi = q_add(s.pm, q_of(ax));                       // hardware-friendly metric
+#else
+    const uint32_t klo = q_add(s.pm, q_of((ax >= 36.7368f) ? 0.0f : t));                       // likely fork
+    const uint32_t khi = q_add(s.pm, q_of((ax >= 709.78271484375f) ? CUDART_INF_F : ax + t));  // unlikely fork
+#endif
+    const uint32_t m0 = neg ? khi : klo, m1 = neg ? klo : khi;
+    const unsigned act = gballot<W>(s.active, gbase);
+    const int A = __popc(act);
+    bool keep0 = s.active, keep1 = s.active;
+    // keep the L best forks under (metric asc, fork index asc)
+    const bool like1 = m1 < m0;                            // likely fork is bit 1
     if constexpr (W == 32) {
         if (2 * A > L) {
             if (A == L) {
@@ -947,8 +943,8 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 const unsigned kb = gmin<W>(s.active ? khi : 0xFFFFFFFFu);
                 const unsigned ka = gmax<W>(s.active ? klo : 0u);
                 if (kb > ka) {
-                    if (s.active) s.pm = mlo;
-                    note_margin<W>(w, __uint_as_float(kb) - __uint_as_float(ka));
+                    if (s.active) s.pm = klo;
+                    note_gap<W>(w, kb - ka, tauq);
                     return like1 ? 1u : 0u;
                 }
             }
@@ -956,29 +952,30 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             unsigned keptA = act, keptB = 0;
             int count = A;
             // margin bookkeeping: last promoted / last demoted metric, and the pair the loop stopped at
-            float kbl = -CUDART_INF_F, kal = CUDART_INF_F, kbn = CUDART_INF_F, kan = -CUDART_INF_F;
+            // (0 and kQSat are the identities of the max / min below)
+            unsigned kbl = 0u, kal = kQSat, kbn = kQSat, kan = 0u;
             while (true) {
                 const unsigned candB = act & ~keptB;
                 if (candB == 0) {                          // every unlikely fork was kept
-                    kan = __uint_as_float(gmax<W>(((keptA >> lane) & 1u) ? klo : 0u));
+                    kan = gmax<W>(((keptA >> lane) & 1u) ? klo : 0u);
                     break;
                 }
                 const unsigned kb = gmin<W>(((candB >> lane) & 1u) ? khi : 0xFFFFFFFFu);
                 const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
                 const int bl = __ffs(eqb) - 1;             // lowest lane = lowest fork index among equals
-                if (count < L) { keptB |= 1u << bl; ++count; kbl = __uint_as_float(kb); continue; }
+                if (count < L) { keptB |= 1u << bl; ++count; kbl = kb; continue; }
                 const unsigned ka = gmax<W>(((keptA >> lane) & 1u) ? klo : 0u);
                 const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
                 const int al = 31 - __clz(eqa);            // highest lane = highest fork index among equals
                 const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
                 const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
                 const bool better = (kb < ka) || (kb == ka && idxb < idxa);
-                if (!better) { kbn = __uint_as_float(kb); kan = __uint_as_float(ka); break; }
+                if (!better) { kbn = kb; kan = ka; break; }
                 keptB |= 1u << bl;
                 keptA &= ~(1u << al);
-                kbl = __uint_as_float(kb); kal = __uint_as_float(ka);
+                kbl = kb; kal = ka;
             }
-            note_margin<W>(w, fminf(kbn, kal) - fmaxf(kan, kbl));   // best dropped fork - worst kept fork
+            note_gap<W>(w, min(kbn, kal) - max(kan, kbl), tauq);     // best dropped fork - worst kept fork
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -989,7 +986,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
         unsigned keptA = act, keptB = 0;
         int count = A;
         bool done = !(2 * A > L);
-        float kbl = -CUDART_INF_F, kal = CUDART_INF_F, kbn = CUDART_INF_F, kan = -CUDART_INF_F;   // as above
+        unsigned kbl = 0u, kal = kQSat, kbn = kQSat, kan = 0u;   // as above
         while (true) {
             const unsigned candB = act & ~keptB;
             if (!__any_sync(FULL_MASK, !done)) break;
@@ -999,23 +996,23 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             const unsigned ka = gmax<W>(ca ? klo : 0u);
             const unsigned eqa = gballot<W>(ca && klo == ka, gbase);
             if (!done) {
-                if (candB == 0) { done = true; kan = __uint_as_float(ka); }       // every unlikely fork was kept
+                if (candB == 0) { done = true; kan = ka; }       // every unlikely fork was kept
                 else {
                     const int bl = __ffs(eqb) - 1;
-                    if (count < L) { keptB |= 1u << bl; ++count; kbl = __uint_as_float(kb); }
+                    if (count < L) { keptB |= 1u << bl; ++count; kbl = kb; }
                     else {
                         const int al = 31 - __clz(eqa);
                         const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
                         const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
                         const bool better = (kb < ka) || (kb == ka && idxb < idxa);
-                        if (!better) { done = true; kbn = __uint_as_float(kb); kan = __uint_as_float(ka); }
-                        else { keptB |= 1u << bl; keptA &= ~(1u << al); kbl = __uint_as_float(kb); kal = __uint_as_float(ka); }
+                        if (!better) { done = true; kbn = kb; kan = ka; }
+                        else { keptB |= 1u << bl; keptA &= ~(1u << al); kbl = kb; kal = ka; }
                     }
                 }
             }
         }
         if (2 * A > L) {
-            note_margin<W>(w, fminf(kbn, kal) - fmaxf(kan, kbl));
+            note_gap<W>(w, min(kbn, kal) - max(kan, kbl), tauq);
             const bool ka_ = (keptA >> slot) & 1u, kb_ = (keptB >> slot) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1045,14 +1042,14 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     __syncwarp();
     src_lane = w.srcof[lane];
     const bool is_new = (src_lane != lane);
-    const float src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
+    const uint32_t src_m1 = __shfl_sync(FULL_MASK, m1, src_lane);
     const unsigned long long src_px = __shfl_sync(FULL_MASK, s.px, src_lane);
     const unsigned long long src_ps = __shfl_sync(FULL_MASK, s.ps, src_lane);
     const uint32_t src_sreg = __shfl_sync(FULL_MASK, s.sreg, src_lane);
     if (is_new) {
         s.active = true; s.pm = src_m1; u = 1u; s.px = src_px; s.ps = src_ps; s.sreg = src_sreg;
     } else if (kill) {
-        s.active = false; s.pm = 0.0f;
+        s.active = false; s.pm = 0u;
     } else if (s.active) {
         u = keep0 ? 0u : 1u;
         s.pm = keep0 ? m0 : m1;
@@ -1093,15 +1090,6 @@ __device__ __forceinline__ void update_partial_sums(const Warp& w, Lane& s, int 
         // every other odd leaf closes only a pair: [left ^ right | right] into the 2-bit field of layer NLOG-1
         const uint32_t P2 = ((s.sreg ^ u) & 1u) | (u << 1);
         s.sreg = (s.sreg & ~6u) | (P2 << 1);
-        return;
-    }
-#endif
-#if POLAR_PS_SHORTCUT >= 2
-    if ((phi & 7) == 3) {
-        // EXPERIMENT (not the default, untested on hardware): a quarter of the odd leaves close a group of four
-        const uint32_t P2 = ((s.sreg ^ u) & 1u) | (u << 1);
-        const uint32_t P4 = (((s.sreg >> 1) ^ P2) & 3u) | (P2 << 2);
-        s.sreg = (s.sreg & ~0x78u) | (P4 << 3);
         return;
     }
 #endif
@@ -1188,9 +1176,9 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         const int last_g = (a.B - 1 - grp * G) < (G - 1) ? (a.B - 1 - grp * G) : (G - 1);
         Lane s;
         s.active = valid && (slot == c0);
-        s.pm = 0.0f; s.px = 0; s.ps = 0; s.sreg = 0;
+        s.pm = 0u; s.px = 0; s.ps = 0; s.sreg = 0;
         w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
-        w.mg[lane] = 0x7F800000u;                       // decision margin so far: +inf
+        w.mg[lane] = kQSat;                             // smallest decision margin so far: none recorded
         __syncwarp();
         int sp = L - 1;
         float lam_n = 0.0f;
@@ -1205,7 +1193,9 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
 
         bool have_x4 = false;
         if (W == 32 && a.PA > 0) {
-            s.pm = phase_a<C>(w, a.PA, c0);              // out of line: runs once per codeword
+            // out of line, runs once per codeword. The metric of the frozen prefix is common to every path that will ever
+            // exist, so it is dropped (only its +inf case, PolarCode.cpp:483 with exp overflowing, is kept: saturated)
+            s.pm = (phase_a<C>(w, a.PA, c0) < CUDART_INF_F) ? 0u : kQSat;
             const float* x4src = w.xs + C::XS_FLOATS + C::MT;
 #pragma unroll
             for (int i = 0; i < 16; ++i) r.x4[i] = x4src[i];
@@ -1217,6 +1207,11 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         for (int phi0 = (W == 32 ? a.PA : 0); phi0 < N; phi0 += 16) {
             if (!have_x4) descend_block<C>(w, s, r, phi0, c0, valid, first_row, last_g);
             have_x4 = false;
+            if constexpr (W != 1) {
+                // renormalise: metrics are kept relative to the best path of the list (exact integer subtraction)
+                const uint32_t base = gmin<W>(s.active ? s.pm : kQSat);
+                if (s.active && s.pm != kQSat) s.pm -= base;
+            }
             const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
             if constexpr (POLAR_UNROLL2 && (W == 32 || W == 1)) {
             // (measured: +3..4 % with one codeword per warp and for plain SC, -7 % at list 4, whose selection loop is larger)
@@ -1240,10 +1235,10 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 }
                 uint32_t u = 0;
                 if ((frozen16 >> j) & 1u) {
-                    if (s.active) s.pm += softplus_ref(-lam_n);          // PolarCode.cpp:475-487
+                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_ref(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
-                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane);
+                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
                     if (permuted) {
                         // a cloned path takes over its parent's subtree registers -- those that are still live:
                         // x4 is read again at leaf 8, x3 at leaves 4 and 12, x2 at leaves 2 mod 4, x1 at odd leaves
@@ -1293,10 +1288,10 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 }
                 uint32_t u = 0;
                 if ((frozen16 >> j) & 1u) {
-                    if (s.active) s.pm += softplus_ref(-lam_n);          // PolarCode.cpp:475-487
+                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_ref(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
-                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane);
+                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
                     if (permuted) {
                         // a cloned path takes over its parent's live subtree registers
 #pragma unroll
@@ -1397,22 +1392,26 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         const unsigned act = gballot<W>(s.active, gbase);
         const unsigned passm = gballot<W>(s.active && pass, gbase);
         const bool use_parity = (a.crc != 0) && (passm != 0);
-        const bool eligible = s.active && (use_parity ? pass : true) && (s.pm < CUDART_INF_F);
-        const unsigned best = gmin<W>(eligible ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
-        const unsigned cand = gballot<W>(eligible && __float_as_uint(s.pm) == best, gbase);
+        const bool eligible = s.active && (use_parity ? pass : true) && (W == 1 || s.pm != kQSat);
+        const unsigned best = gmin<W>(eligible ? s.pm : 0xFFFFFFFFu);
+        const unsigned cand = gballot<W>(eligible && s.pm == best, gbase);
         const int win = cand ? (__ffs(cand) - 1) : 0;
         const bool win_active = (act >> win) & 1u;
         __syncwarp();
+        bool flagme = false;
         if (a.margin != nullptr || a.flag_list != nullptr) {
-            // the final pick is a decision too: runner-up metric - winner's metric (0 when two paths tie)
-            float mgv = __uint_as_float(w.mg[w.g]);
+            // the final pick is a decision too: runner-up metric - winner's metric (0 when two paths tie, or when every
+            // candidate is saturated and the reference's choice cannot be reproduced from these metrics)
+            uint32_t mgq = w.mg[w.g];
             if constexpr (W > 1) {
-                const unsigned second = gmin<W>((eligible && slot != win) ? __float_as_uint(s.pm) : 0xFFFFFFFFu);
-                if (cand != 0 && second != 0xFFFFFFFFu) mgv = fminf(mgv, __uint_as_float(second) - __uint_as_float(best));
+                const unsigned second = gmin<W>((eligible && slot != win) ? s.pm : 0xFFFFFFFFu);
+                if (cand == 0) mgq = 0u;
+                else if (second != 0xFFFFFFFFu) mgq = min(mgq, second - best);
             }
+            flagme = a.flag_list != nullptr && mgq < a.tauq_flag;
             if (slot == 0 && valid) {
-                if (a.margin != nullptr) a.margin[a.cw_base + cw] = mgv;
-                if (a.flag_list != nullptr && mgv < a.tau) a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;
+                if (a.margin != nullptr) a.margin[a.cw_base + cw] = (mgq == kQSat) ? CUDART_INF_F : (float)mgq * (1.0f / kQScale);
+                if (flagme) a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;
             }
         }
 #pragma unroll 1
@@ -1421,6 +1420,8 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             if (cwg >= a.B) break;
             const int wl = g * W + __shfl_sync(FULL_MASK, win, g * W);
             const bool wa = __shfl_sync(FULL_MASK, (int)win_active, g * W);
+            const bool fl = __shfl_sync(FULL_MASK, (int)flagme, g * W);
+            bool differs = false;                            // from the transmitted info bits (a.truth)
             const uint32_t* U = sbase<C, 0>(w) + wl;
 #if POLAR_TAIL_REGS
             // the winner's u-hat spread over the lanes (word 32 q + lane in uw[q]); a bit lookup is then a shuffle,
@@ -1445,7 +1446,11 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                     }
                     if (i < jmax) word |= ((v >> (pos & 31)) & 1u) << i;
                 }
-                if (t < KW) a.out[(size_t)cwg * KW + t] = wa ? word : 0u;
+                if (t < KW) {
+                    if (!wa) word = 0u;
+                    if (a.out != nullptr) a.out[(size_t)cwg * KW + t] = word;
+                    if (a.truth != nullptr) differs |= word != a.truth[(size_t)cwg * KW + t];
+                }
             }
 #else
             for (int t = lane; t < KW; t += 32) {           // decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174
@@ -1457,9 +1462,15 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                         word |= ((U[(pos >> 5) * 32] >> (pos & 31)) & 1u) << i;
                     }
                 }
-                a.out[(size_t)cwg * KW + t] = word;
+                if (a.out != nullptr) a.out[(size_t)cwg * KW + t] = word;
+                if (a.truth != nullptr) differs |= word != a.truth[(size_t)cwg * KW + t];
             }
 #endif
+            if (a.truth != nullptr) {                        // PolarCode.cpp:758-769
+                const bool block_error = __any_sync(FULL_MASK, differs);
+                if (lane == 0 && block_error && !fl)
+                    atomicAdd(a.err + (int)((unsigned long long)(a.first_index + a.cw_base + cwg) % (unsigned)a.n_ebno), 1ull);
+            }
         }
         __syncwarp();
     }
@@ -1472,4 +1483,4 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
     }
 }
 
-}  // namespace fast
+}  // namespace POLAR_FAST_NS

@@ -15,6 +15,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PORT_SO = os.path.join(ROOT, "oracle", "_build", "libpolar_oracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libpolar_ref.so")
+REF_O3_SO = os.path.join(ROOT, "oracle", "_ref", "libpolar_ref_o3.so")      # same sources, -O3 -march=native of the build host
 REF_MAIN = os.path.join(ROOT, "oracle", "_ref", "polar_ref_main")
 
 _u8p = np.ctypeslib.ndpointer(np.uint8, flags="C_CONTIGUOUS")
@@ -33,6 +34,23 @@ def build_port():
 
 def have_ref():
     return os.path.exists(REF_SO)
+
+
+def have_ref_o3():
+    """the -O3 -march=native build exists AND this host has every ISA extension it was compiled for"""
+    flags_file = os.path.join(os.path.dirname(REF_O3_SO), "o3_flags.txt")
+    if not (os.path.exists(REF_O3_SO) and os.path.exists(flags_file)):
+        return False
+    try:
+        need = set(open(flags_file).read().split())
+        have = set()
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("flags"):
+                have = set(line.split(":", 1)[1].split())
+                break
+        return need <= have
+    except OSError:
+        return False
 
 
 class _Base:
@@ -145,8 +163,8 @@ class Port(_Base):
 class Ref(_Base):
     prefix = "ref_"
 
-    def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True):
-        lib = C.CDLL(REF_SO)
+    def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True, so=None):
+        lib = C.CDLL(so or REF_SO)
         super().__init__(lib, n, K, epsilon, crc, reseed)
         lib.ref_decode_batch.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _u8p, C.c_int]
 

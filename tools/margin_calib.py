@@ -37,8 +37,10 @@ for (n, K, crc, L, eb, B) in settings:
     reps = max(1, 65536 // B)
     big = d_llr.repeat(reps, 1).contiguous()
     out = torch.empty((big.shape[0], pc.KW), dtype=torch.int32, device="cuda")
-    tim = {}
-    for mode in ("fp32", "strict"):
+    tim, flagged_at = {}, {}
+    for mode, tau in (("fp32", None), ("strict", 1e-6), ("strict", 3e-6), ("strict", 1e-5), ("strict", 3e-5)):
+        if tau is not None:
+            pc.set_strict_tau(tau)
         for _ in range(2):
             pc.decode_device(big, L, out=out, mode=mode)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -46,15 +48,18 @@ for (n, K, crc, L, eb, B) in settings:
         for _ in range(3):
             pc.decode_device(big, L, out=out, mode=mode)
         e1.record(); torch.cuda.synchronize()
-        tim[mode] = big.shape[0] * 3 / (e0.elapsed_time(e1) * 1e-3)
-    flagged_big = pc.last_flagged
+        key = mode if tau is None else "strict@%g" % tau
+        tim[key] = big.shape[0] * 3 / (e0.elapsed_time(e1) * 1e-3)
+        if tau is not None:
+            flagged_at[key] = pc.last_flagged
+    flagged_big = flagged_at
     row = dict(n=n, K=K, crc=crc, L=L, ebno=eb, B=B, cpu=type(cpu).__name__, cpu_cw_per_s=B / tc,
                mismatch_fp32=int(mm.sum()), margins_of_mismatches=sorted(float(x) for x in m[mm]),
                mismatch_strict_device=int(mm_strict.sum()), mismatch_strict_host=int(mm_host.sum()),
                mismatch_strict_double_entry=int(mm_dbl.sum()), flagged_at_default_tau=int(nflag),
                flag_share={"%g" % t: float((m < t).mean()) for t in TAUS},
                margin_quantiles={q: float(np.quantile(m[np.isfinite(m)], q)) for q in (0.001, 0.01, 0.1, 0.5)} if np.isfinite(m).any() else {},
-               cw_per_s_fp32=tim["fp32"], cw_per_s_strict=tim["strict"], flagged_in_timing_batch=int(flagged_big),
+               cw_per_s=tim, flagged_in_timing_batch=flagged_big,
                timing_batch=int(big.shape[0]), block_errors_ref=int((want != info).any(1).sum()))
     rows.append(row)
     print(json.dumps(row), flush=True)
