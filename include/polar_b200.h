@@ -42,8 +42,10 @@ enum {
     POLAR_B200_E_ARG = -1,        /* null pointer / out-of-range argument            */
     POLAR_B200_E_UNSUPPORTED = -2,/* valid for the reference, not for this build     */
     POLAR_B200_E_NOGPU = -3,      /* no usable CUDA device: there is NO CPU fallback */
-    POLAR_B200_E_BATCH = -4,      /* B exceeds the ctx's max_batch                   */
-    POLAR_B200_E_LIST = -5        /* list size < 1, > max_list or > 127              */
+    POLAR_B200_E_BATCH = -4,      /* (ABI 1: B exceeded max_batch; staging now grows on demand, no longer returned) */
+    POLAR_B200_E_LIST = -5,       /* list size < 1, > max_list or > 127              */
+    POLAR_B200_E_NONCCL = -6,     /* libnccl.so.2 not loadable (polar_b200_comm_* only) */
+    POLAR_B200_E_NCCL = -7        /* an NCCL call failed                             */
 };
 
 /* ABI version of this header; polar_b200_abi_version() must return the same value. */
@@ -73,6 +75,9 @@ const char* polar_b200_strerror(int code);
 
 /* Words of packed output per codeword: ceil(K/32). */
 int polar_b200_info_words(int K);
+
+/* CUDA devices visible to this process (0 when there is none). */
+int polar_b200_device_count(void);
 
 /*
  * Create a decoder for one polar code on one device.
@@ -205,6 +210,36 @@ int polar_b200_count_errors(polar_b200_ctx* ctx, const uint32_t* info_packed,
 int polar_b200_synthesize(polar_b200_ctx* ctx, unsigned long long seed, long long first_index, int B,
                           const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed,
                           void* cuda_stream);
+
+/*
+ * Monte-Carlo BLER sweep on this ctx's device: the codewords with global indices first_index .. first_index+count-1
+ * (codeword g at Eb/N0 point g % n_ebno, as in polar_b200_synthesize) are synthesised, decoded with every list size and
+ * compared with the transmitted info bits on the device, chunk by chunk; only the counters come back. Replaces the body
+ * of the reference's BLER loop (PolarCode.cpp:696-775: generation :703-716, :744-753, decode :756, comparison :758-769)
+ * without its sequential early-stop shortcuts (:725-742). Per chunk and list size this is one decode launch with the
+ * block-error count fused into its tail (plus, in STRICT mode, the second pass over the flagged codewords).
+ *   lists   host, [n_list] list sizes;  mode  POLAR_B200_MODE_*
+ *   counts  host, [n_list][n_ebno][2] out: (num_err, num_run) per cell, to be summed over shards
+ * Synchronous. Shards of one sweep (other devices / ranks) use the same seed and disjoint index ranges.
+ */
+int polar_b200_bler_sweep(polar_b200_ctx* ctx, unsigned long long seed, long long first_index, long long count,
+                          const double* ebno_db, int n_ebno, const int* lists, int n_list, int mode,
+                          long long* counts, void* cuda_stream);
+
+/*
+ * The one collective of a sharded sweep: sum the int64 counters over GPUs with ncclAllReduce.
+ * One communicator per GPU: either one process per GPU (rank 0 calls polar_b200_comm_unique_id, the 128 bytes travel
+ * by any means, every rank calls polar_b200_comm_init_rank) or one process driving several GPUs
+ * (polar_b200_comm_init_all fills comms[ndev]; polar_b200_comm_allreduce_i64_group reduces all of them in one NCCL group).
+ * values: host vectors, summed in place. libnccl.so.2 is loaded at run time (POLAR_B200_E_NONCCL if absent).
+ */
+typedef struct polar_b200_comm polar_b200_comm;
+int polar_b200_comm_unique_id(unsigned char* id128);
+int polar_b200_comm_init_rank(polar_b200_comm** out, int device, int nranks, int rank, const unsigned char* id128);
+int polar_b200_comm_init_all(polar_b200_comm** comms, int ndev, const int* devices);
+int polar_b200_comm_allreduce_i64(polar_b200_comm* comm, long long* values, int n);
+int polar_b200_comm_allreduce_i64_group(polar_b200_comm** comms, int ncomm, long long** values, int n);
+int polar_b200_comm_destroy(polar_b200_comm* comm);
 
 /* Introspection (all return -1 for an unknown key). */
 enum {

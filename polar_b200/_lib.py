@@ -49,6 +49,14 @@ def dev():
         lib.polar_b200_decode_scl_p1.argtypes = [vp, vp, vp, ip, ip, vp, vp]
         lib.polar_b200_decode_scl_p1_host.argtypes = [vp, vp, vp, ip, ip, vp, vp]
         lib.polar_b200_synthesize.argtypes = [vp, C.c_ulonglong, C.c_longlong, ip, vp, ip, vp, vp, vp]
+        lib.polar_b200_bler_sweep.argtypes = [vp, C.c_ulonglong, C.c_longlong, C.c_longlong, vp, ip, vp, ip, ip, vp, vp]
+        lib.polar_b200_device_count.restype = ip
+        lib.polar_b200_comm_unique_id.argtypes = [vp]
+        lib.polar_b200_comm_init_rank.argtypes = [C.POINTER(vp), ip, ip, ip, vp]
+        lib.polar_b200_comm_init_all.argtypes = [vp, ip, vp]
+        lib.polar_b200_comm_allreduce_i64.argtypes = [vp, vp, ip]
+        lib.polar_b200_comm_allreduce_i64_group.argtypes = [vp, ip, vp, ip]
+        lib.polar_b200_comm_destroy.argtypes = [vp]
         lib.polar_b200_get_info.restype = C.c_longlong
         lib.polar_b200_get_info.argtypes = [vp, ip]
         _dev = lib
@@ -81,6 +89,7 @@ def host():
         lib.polar_host_ctx.restype = vp
         lib.polar_host_ctx.argtypes = [vp, ip]
         lib.polar_host_get_bler_quick.argtypes = [vp, vp, ip, vp, ip, ip, ip, ip, vp]
+        lib.polar_host_bler_sweep.argtypes = [vp, vp, ip, vp, ip, C.c_longlong, C.c_ulonglong, vp, ip, vp]
         _host = lib
     return _host
 

@@ -35,27 +35,45 @@ def sweep_counts(code, decode_fn, list_sizes, ebno_db, total, seed, rank=0, worl
     return counts
 
 
-def sweep_counts_device(code, list_sizes, ebno_db, total, seed, rank=0, world=1, chunk=65536):
-    """Same counters with everything on the GPU: codewords are synthesised on the device
-    (polar_b200_synthesize), decoded and compared there; only the counters come back.
-    `total` codewords PER Eb/N0 point, split over ranks; point ie uses seed + ie."""
-    import torch
-    counts = np.zeros((len(list_sizes), len(ebno_db), 2), np.int64)
-    lo = total * rank // world
-    hi = total * (rank + 1) // world
-    dev = torch.device("cuda", code.device)
-    nerr = torch.zeros(1, dtype=torch.int64, device=dev)
-    for ie, eb in enumerate(ebno_db):
-        for first in range(lo, hi, chunk):
-            nb = min(chunk, hi - first)
-            llr, truth = code.synthesize(nb, [eb], seed + ie, first_index=first)
-            for il, L in enumerate(list_sizes):
-                out = code.decode_device(llr, int(L))
-                nerr.zero_()
-                code.count_errors(out, truth, None, nerr)
-                counts[il, ie, 0] += int(nerr.item())
-                counts[il, ie, 1] += nb
-    return counts
+def sweep_counts_device(code, list_sizes, ebno_db, total, seed, rank=0, world=1, mode=None):
+    """Same counters with everything on the GPU (a binding of polar_b200_bler_sweep): `total` codewords PER Eb/N0 point;
+    the interleaved index space [0, total * len(ebno_db)) is split over ranks in contiguous blocks, every rank synthesises,
+    decodes and compares its block on its device, only the counters come back."""
+    n_pts = len(ebno_db)
+    all_cw = total * n_pts
+    lo = all_cw * rank // world
+    hi = all_cw * (rank + 1) // world
+    return code.bler_sweep_device(ebno_db, list_sizes, hi - lo, seed, first_index=lo, mode=mode)
+
+
+class Comm:
+    """The C++ side's NCCL communicator (polar_b200_comm_*), one per process and GPU: the collective of a sharded sweep is
+    ncclAllReduce over the int64 counters. Bootstrap: rank 0's unique id reaches the other ranks through `exchange`,
+    a callable bytes -> bytes that broadcasts rank 0's value (e.g. over torch.distributed)."""
+
+    def __init__(self, device, world, rank, exchange):
+        import ctypes as C
+        from . import _lib
+        lib = _lib.dev()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(lib.polar_b200_comm_unique_id(buf))
+        ident = exchange(bytes(buf))
+        self._h = C.c_void_p()
+        _lib.check(lib.polar_b200_comm_init_rank(C.byref(self._h), int(device), int(world), int(rank),
+                                                 (C.c_ubyte * 128).from_buffer_copy(ident)))
+
+    def all_reduce(self, counts):
+        from . import _lib
+        out = np.ascontiguousarray(counts, np.int64).copy()
+        _lib.check(_lib.dev().polar_b200_comm_allreduce_i64(self._h, out.ctypes.data, out.size))
+        return out
+
+    def close(self):
+        from . import _lib
+        if self._h:
+            _lib.dev().polar_b200_comm_destroy(self._h)
+            self._h = None
 
 
 def all_reduce_counts(counts, device=None):

@@ -227,6 +227,31 @@ class PolarCode:
                                                     C.c_void_p(stream)))
         return llr, truth
 
+    def bler_sweep_device(self, ebno_db, list_sizes, count, seed, first_index=0, mode=None):
+        """polar_b200_bler_sweep on this object's device: `count` codewords from global index first_index (codeword g at
+        point g % len(ebno_db)) synthesised, decoded and compared on the GPU. Returns int64 [lists][ebno][2] = (num_err,
+        num_run) of this shard."""
+        eb = np.ascontiguousarray(np.atleast_1d(ebno_db), np.float64)
+        ls = np.ascontiguousarray(np.atleast_1d(list_sizes), np.int32)
+        counts = np.zeros((len(ls), len(eb), 2), np.int64)
+        m = MODES[self.mode if mode is None else mode] if not isinstance(mode, int) else mode
+        _lib.check(_lib.dev().polar_b200_bler_sweep(self.ctx(1), int(seed) & (2**64 - 1), int(first_index), int(count),
+                                                    eb.ctypes.data, len(eb), ls.ctypes.data, len(ls), m, counts.ctypes.data, None))
+        return counts
+
+    def bler_sweep(self, ebno_db, list_sizes, total, seed=1, devices=None):
+        """PolarCode::bler_sweep (C++): the index range [0, total) sharded over `devices` (default all visible), one host
+        thread per device, counters summed with ncclAllReduce. Returns (bler [lists][ebno], counts [lists][ebno][2])."""
+        eb = np.ascontiguousarray(np.atleast_1d(ebno_db), np.float64)
+        ls = np.ascontiguousarray(np.atleast_1d(list_sizes), np.uint8)
+        counts = np.zeros((len(ls), len(eb), 2), np.int64)
+        dv = np.ascontiguousarray(devices, np.int32) if devices is not None else None
+        _lib.check_host(_lib.host().polar_host_bler_sweep(self._h, eb.ctypes.data, len(eb), ls.ctypes.data, len(ls), int(total),
+                                                          int(seed) & (2**64 - 1), dv.ctypes.data if dv is not None else None,
+                                                          len(dv) if dv is not None else 0, counts.ctypes.data))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return counts[..., 0] / counts[..., 1], counts
+
     def ctx(self, min_batch=1):
         c = _lib.host().polar_host_ctx(self._h, int(min_batch))
         if not c:

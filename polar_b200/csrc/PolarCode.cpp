@@ -11,6 +11,7 @@
 #include <random>
 #include <stdexcept>
 #include <string>
+#include <thread>
 
 #include "polar_b200.h"
 
@@ -274,6 +275,64 @@ std::vector<std::vector<double>> PolarCode::get_bler_quick(std::vector<double> e
     return bler;
 }
 
+// The multi-GPU form of the BLER loop (PolarCode.cpp:696-775): shards of the codeword index space on every device,
+// the counters reduced with ncclAllReduce.
+std::vector<std::vector<double>> PolarCode::bler_sweep(const std::vector<double>& ebno_vec, const std::vector<uint8_t>& list_size,
+                                                       long long total, unsigned long long seed, std::vector<int> devices,
+                                                       std::vector<long long>* counts_out) {
+    const int ne = (int)ebno_vec.size(), nl = (int)list_size.size();
+    if (ne < 1 || nl < 1 || total < 0) throw std::invalid_argument("PolarCode::bler_sweep: empty sweep");
+    if (devices.empty()) {
+        const int nd = polar_b200_device_count();
+        if (nd < 1) throw std::runtime_error("PolarCode::bler_sweep: no CUDA device (there is no CPU fallback)");
+        for (int d = 0; d < nd; ++d) devices.push_back(d);
+    }
+    const int nd = (int)devices.size();
+    std::vector<int> lists(list_size.begin(), list_size.end());
+    for (int L : lists) if (L < 1 || L >= 128) throw std::invalid_argument("PolarCode: list_size must be in 1..127");
+    std::vector<uint8_t> flat((size_t)_crc_size * _info_length);
+    for (int r = 0; r < _crc_size; ++r)
+        std::copy(_crc_matrix[r].begin(), _crc_matrix[r].end(), flat.begin() + (size_t)r * _info_length);
+    const size_t cells = (size_t)nl * ne * 2;
+    std::vector<std::vector<long long>> local(nd, std::vector<long long>(cells, 0));
+    std::vector<polar_b200_ctx*> ctxs(nd, nullptr);
+    std::vector<int> rcs(nd, 0);
+    std::vector<std::thread> workers;
+    for (int d = 0; d < nd; ++d)
+        workers.emplace_back([&, d] {
+            // this device's shard: a contiguous block of the global index space
+            const long long lo = total * d / nd, hi = total * (d + 1) / nd;
+            int rc = polar_b200_create(&ctxs[d], devices[d], _n, _info_length, _crc_size, _frozen_bits.data(),
+                                       _channel_order_descending.data(), _crc_size ? flat.data() : nullptr, 127, 1);
+            if (!rc) rc = polar_b200_bler_sweep(ctxs[d], seed, lo, hi - lo, ebno_vec.data(), ne, lists.data(), nl, arithmetic_mode,
+                                                local[d].data(), nullptr);
+            rcs[d] = rc;
+        });
+    for (auto& w : workers) w.join();
+    int first_rc = 0;
+    for (int d = 0; d < nd; ++d) { if (ctxs[d]) polar_b200_destroy(ctxs[d]); if (rcs[d] && !first_rc) first_rc = rcs[d]; }
+    check(first_rc, "polar_b200_bler_sweep");
+    // the one collective: sum of the counters over the devices
+    std::vector<polar_b200_comm*> comms(nd, nullptr);
+    int rc = polar_b200_comm_init_all(comms.data(), nd, devices.data());
+    if (rc == POLAR_B200_E_NONCCL && nd == 1) rc = POLAR_B200_OK;        // a single device has nothing to reduce
+    else if (!rc) {
+        std::vector<long long*> ptrs(nd);
+        for (int d = 0; d < nd; ++d) ptrs[d] = local[d].data();
+        rc = polar_b200_comm_allreduce_i64_group(comms.data(), nd, ptrs.data(), (int)cells);
+    }
+    for (auto* m : comms) if (m) polar_b200_comm_destroy(m);
+    check(rc, "polar_b200_comm_allreduce_i64_group");
+    std::vector<std::vector<double>> bler(nl, std::vector<double>(ne, 0.0));
+    for (int il = 0; il < nl; ++il)
+        for (int ie = 0; ie < ne; ++ie) {
+            const long long e = local[0][((size_t)il * ne + ie) * 2], r = local[0][((size_t)il * ne + ie) * 2 + 1];
+            bler[il][ie] = r ? (double)e / (double)r : 0.0;
+        }
+    if (counts_out) *counts_out = local[0];
+    return bler;
+}
+
 // ---------------------------------------------------------------------------------------------
 // C wrappers so the Python package (ctypes) can drive the host class. Exceptions are turned into
 // a thread-local message + nonzero return.
@@ -379,6 +438,18 @@ void* polar_host_ctx(void* h, int min_batch) {
     void* c = nullptr;
     if (guarded([&] { c = p->device_ctx(min_batch); })) return nullptr;
     return c;
+}
+
+// counts: [n_list][n_ebno][2] int64 out (reduced over the devices); devices may be NULL (= all visible)
+int polar_host_bler_sweep(void* h, const double* ebno, int n_ebno, const uint8_t* lists, int n_list, long long total,
+                          unsigned long long seed, const int* devices, int n_devices, long long* counts) {
+    PolarCode* p = static_cast<PolarCode*>(h);
+    return guarded([&] {
+        std::vector<long long> c;
+        p->bler_sweep(std::vector<double>(ebno, ebno + n_ebno), std::vector<uint8_t>(lists, lists + n_list), total, seed,
+                      devices ? std::vector<int>(devices, devices + n_devices) : std::vector<int>(), &c);
+        std::copy(c.begin(), c.end(), counts);
+    });
 }
 
 int polar_host_get_bler_quick(void* h, const double* ebno, int n_ebno, const uint8_t* lists, int n_list,

@@ -55,6 +55,16 @@ public:
     void decode_scl_llr_device(const float* llr_dev, int B, uint16_t list_size, uint32_t* info_packed_dev, void* cuda_stream,
                                float* margin_dev = nullptr);
 
+    // Monte-Carlo BLER over `total` codewords (codeword g at Eb/N0 point g % ebno_vec.size()), generated, decoded and
+    // compared on the GPUs: the index range is split over `devices` (default: every visible device), one host thread and
+    // one decoder context per device, and the (num_err, num_run) counters are summed with ncclAllReduce. No early stop,
+    // unlike get_bler_quick (PolarCode.cpp:725-742 is sequential in run order); result[list][ebno] = num_err / num_run.
+    // counts (optional): [list][ebno][2] receives the reduced counters.
+    std::vector<std::vector<double>> bler_sweep(const std::vector<double>& ebno_vec, const std::vector<uint8_t>& list_size,
+                                                long long total, unsigned long long seed = 1,
+                                                std::vector<int> devices = std::vector<int>(),
+                                                std::vector<long long>* counts = nullptr);
+
     int block_length() const { return _block_length; }
     int info_length() const { return _info_length; }
     int crc_size() const { return _crc_size; }

@@ -38,8 +38,21 @@
 #include <string.h>
 #include <math.h>
 
+#include <dlfcn.h>
+
 #include <new>
 #include <vector>
+
+#if __has_include(<nccl.h>)
+#include <nccl.h>
+#else
+// minimal declarations of the NCCL C API (the library itself is loaded at run time, see polar_b200_comm_*)
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef enum { ncclSuccess = 0 } ncclResult_t;
+typedef enum { ncclInt64 = 4 } ncclDataType_t;
+typedef enum { ncclSum = 0 } ncclRedOp_t;
+#endif
 
 #include "polar_b200.h"
 
@@ -531,6 +544,11 @@ struct polar_b200_ctx {
     int* d_flag_count = nullptr;           // [2]: counter of the current call, copy kept for polar_b200_get_info
     int flag_cap = 0;
     float strict_tau = 0.0f;
+    float* d_sw_llr = nullptr;             // polar_b200_bler_sweep: one chunk of synthesised LLRs / info bits / decoded bits
+    uint32_t* d_sw_truth = nullptr;
+    uint32_t* d_sw_out = nullptr;
+    unsigned long long* d_sw_err = nullptr;
+    int sw_chunk = 0, sw_cells = 0;
     double* d_ex_gx = nullptr;             // scratch of the block-per-codeword double decoder (scl_exact.cuh), grow-only
     size_t ex_gx_bytes = 0;
     double* d_cvt = nullptr;               // float -> double conversion buffer of the kernels that take one input type
@@ -1014,6 +1032,28 @@ int decode_f64_from_float(polar_b200_ctx* c, const float* llr, int B, int L, uin
     return decode_generic<double, float>(c, llr, B, L, out, st);
 }
 
+int upload_amplitudes(polar_b200_ctx* c, const double* ebno_db, int n_ebno, cudaStream_t st) {
+    double amp[64];
+    for (int i = 0; i < n_ebno; ++i)      // PolarCode.cpp:744-745
+        amp[i] = pow(10.0, ebno_db[i] / 20.0) * sqrt((double)c->K / (double)c->N);
+    CU_TRY(cudaMemcpyAsync(c->d_amp, amp, n_ebno * sizeof(double), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));    // amp[] is a stack buffer
+    return 0;
+}
+int synth_launch(polar_b200_ctx* c, unsigned long long seed, long long first_index, int B, int n_ebno, float* llr,
+                 uint32_t* truth_packed, cudaStream_t st) {
+    SynthArgs a;
+    a.llr = llr; a.truth = truth_packed; a.inv_order = c->d_inv_order; a.crc_rows = c->d_crc_rows; a.amp = c->d_amp;
+    a.seed = seed; a.first_index = first_index; a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.n_ebno = n_ebno;
+    int blocks = (B + 3) / 4;
+    const int cap = c->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    synth_kernel<<<blocks, 128, 0, st>>>(a);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    return POLAR_B200_OK;
+}
+
 float strict_tau(const polar_b200_ctx* c) {
     const char* e = getenv("POLAR_B200_STRICT_TAU");
     if (e && *e) return (float)atof(e);
@@ -1197,6 +1237,8 @@ const char* polar_b200_strerror(int code) {
         case POLAR_B200_E_NOGPU: return "polar_b200: no usable CUDA device (there is no CPU fallback)";
         case POLAR_B200_E_BATCH: return "polar_b200: batch larger than the ctx's max_batch";
         case POLAR_B200_E_LIST: return "polar_b200: list size must be in 1..min(max_list, 127)";
+        case POLAR_B200_E_NONCCL: return "polar_b200: libnccl.so.2 could not be loaded (needed only by polar_b200_comm_*)";
+        case POLAR_B200_E_NCCL: return "polar_b200: an NCCL call failed";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);
@@ -1204,6 +1246,12 @@ const char* polar_b200_strerror(int code) {
 }
 
 int polar_b200_info_words(int K) { return (K + 31) / 32; }
+
+int polar_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
 
 int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bits,
                       const uint8_t* frozen_mask, const uint16_t* info_order,
@@ -1285,6 +1333,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
     cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt); cudaFree(c->d_ex_gx);
+    cudaFree(c->d_sw_llr); cudaFree(c->d_sw_truth); cudaFree(c->d_sw_out); cudaFree(c->d_sw_err);
     cudaFreeHost(c->h_f32); cudaFreeHost(c->h_list); cudaFreeHost(c->h_gather); cudaFreeHost(c->h_out2);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->st_h2d) {
@@ -1480,20 +1529,203 @@ int polar_b200_synthesize(polar_b200_ctx* c, unsigned long long seed, long long 
     if (B == 0) return POLAR_B200_OK;
     CU_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    double amp[64];
-    for (int i = 0; i < n_ebno; ++i)      // PolarCode.cpp:744-745
-        amp[i] = pow(10.0, ebno_db[i] / 20.0) * sqrt((double)c->K / (double)c->N);
-    CU_TRY(cudaMemcpyAsync(c->d_amp, amp, n_ebno * sizeof(double), cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaStreamSynchronize(st));    // amp[] is a stack buffer
-    SynthArgs a;
-    a.llr = llr; a.truth = truth_packed; a.inv_order = c->d_inv_order; a.crc_rows = c->d_crc_rows; a.amp = c->d_amp;
-    a.seed = seed; a.first_index = first_index; a.B = B; a.n = c->n; a.K = c->K; a.crc = c->crc; a.n_ebno = n_ebno;
-    int blocks = (B + 3) / 4;
-    const int cap = c->sm_count * 16;
-    if (blocks > cap) blocks = cap;
-    synth_kernel<<<blocks, 128, 0, st>>>(a);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
+    int rc = upload_amplitudes(c, ebno_db, n_ebno, st);
+    if (rc) return rc;
+    return synth_launch(c, seed, first_index, B, n_ebno, llr, truth_packed, st);
+}
+
+int polar_b200_bler_sweep(polar_b200_ctx* c, unsigned long long seed, long long first_index, long long count,
+                          const double* ebno_db, int n_ebno, const int* lists, int n_list, int mode,
+                          long long* counts, void* cuda_stream) {
+    if (!c || !ebno_db || !lists || !counts || count < 0 || first_index < 0 || n_ebno < 1 || n_ebno > 64 || n_list < 1)
+        return POLAR_B200_E_ARG;
+    if (mode < POLAR_B200_MODE_FP32 || mode > POLAR_B200_MODE_MINSUM) return POLAR_B200_E_ARG;
+    for (int i = 0; i < n_list; ++i)
+        if (lists[i] < 1 || lists[i] > c->max_list || lists[i] > kMaxList) return POLAR_B200_E_LIST;
+    if (c->K > 2048 || c->N > 8192 || c->crc > 32) return POLAR_B200_E_UNSUPPORTED;
+    CU_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int rc = call_begin(c, st);
+    if (rc) return rc;
+    long long chunk = env_int("POLAR_B200_SWEEP_CHUNK", 65536);
+    if (chunk < 1) chunk = 1;
+    if (chunk > count && count > 0) chunk = count;
+    const int cells = n_list * n_ebno;
+    if ((int)chunk > c->sw_chunk) {
+        drain(c);
+        cudaFree(c->d_sw_llr); cudaFree(c->d_sw_truth); cudaFree(c->d_sw_out);
+        c->d_sw_llr = nullptr; c->d_sw_truth = nullptr; c->d_sw_out = nullptr; c->sw_chunk = 0;
+        CU_TRY(cudaMalloc(&c->d_sw_llr, (size_t)chunk * c->N * sizeof(float)));
+        CU_TRY(cudaMalloc(&c->d_sw_truth, (size_t)chunk * c->KW * sizeof(uint32_t)));
+        CU_TRY(cudaMalloc(&c->d_sw_out, (size_t)chunk * c->KW * sizeof(uint32_t)));
+        c->sw_chunk = (int)chunk;
+    }
+    if (cells > c->sw_cells) {
+        drain(c);
+        cudaFree(c->d_sw_err); c->d_sw_err = nullptr; c->sw_cells = 0;
+        CU_TRY(cudaMalloc(&c->d_sw_err, (size_t)cells * sizeof(unsigned long long)));
+        c->sw_cells = cells;
+    }
+    CU_TRY(cudaMemsetAsync(c->d_sw_err, 0, (size_t)cells * sizeof(unsigned long long), st));
+    if ((rc = upload_amplitudes(c, ebno_db, n_ebno, st))) return rc;
+    // per chunk: one synthesis launch, then per list size one decode launch with the block-error count fused into its
+    // tail (plus strict mode's second pass over the few flagged codewords); nothing but the counters leaves the device
+    for (long long first = first_index; first < first_index + count; first += chunk) {
+        const int nb = (int)((first_index + count - first) < chunk ? (first_index + count - first) : chunk);
+        if ((rc = synth_launch(c, seed, first, nb, n_ebno, c->d_sw_llr, c->d_sw_truth, st))) return rc;
+        for (int il = 0; il < n_list; ++il) {
+            CountSpec cs;
+            cs.truth = c->d_sw_truth; cs.err = c->d_sw_err + (size_t)il * n_ebno; cs.first_index = first; cs.n_ebno = n_ebno;
+            if ((rc = decode_mode(c, c->d_sw_llr, nb, lists[il], c->d_sw_out, mode, nullptr, st, -2, 0, true, true, &cs))) return rc;
+        }
+    }
+    std::vector<unsigned long long> err((size_t)cells);
+    CU_TRY(cudaMemcpyAsync(err.data(), c->d_sw_err, (size_t)cells * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    c->have_last = false;
+    for (int il = 0; il < n_list; ++il)
+        for (int ie = 0; ie < n_ebno; ++ie) {
+            // codewords g in [first_index, first_index + count) with g % n_ebno == ie
+            const long long lo = first_index, hi = first_index + count;
+            auto upto = [&](long long x) { return x <= ie ? 0 : (x - ie + n_ebno - 1) / n_ebno; };   // #{g < x : g % n_ebno == ie}
+            counts[((size_t)il * n_ebno + ie) * 2 + 0] = (long long)err[(size_t)il * n_ebno + ie];
+            counts[((size_t)il * n_ebno + ie) * 2 + 1] = upto(hi) - upto(lo);
+        }
+    return POLAR_B200_OK;
+}
+
+// ---- NCCL: only the (num_err, num_run) counters of a sharded sweep cross GPUs ----
+// libnccl is loaded at run time (the copy a host framework already has in the process, else the system one), so this
+// library has no link-time dependency on it.
+struct polar_b200_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0, nranks = 1, rank = 0;
+    long long* d_buf = nullptr;
+    size_t cap = 0;
+    cudaStream_t st = nullptr;
+};
+
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    bool ok = false;
+};
+const NcclApi& nccl_api() {
+    static NcclApi api = [] {
+        NcclApi a;
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(a.lib, "ncclCommInitRank");
+        a.CommInitAll = (decltype(a.CommInitAll))dlsym(a.lib, "ncclCommInitAll");
+        a.AllReduce = (decltype(a.AllReduce))dlsym(a.lib, "ncclAllReduce");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(a.lib, "ncclCommDestroy");
+        a.GroupStart = (decltype(a.GroupStart))dlsym(a.lib, "ncclGroupStart");
+        a.GroupEnd = (decltype(a.GroupEnd))dlsym(a.lib, "ncclGroupEnd");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommInitAll && a.AllReduce && a.CommDestroy && a.GroupStart && a.GroupEnd;
+        return a;
+    }();
+    return api;
+}
+int comm_buffer(polar_b200_comm* m, size_t n) {
+    if (n <= m->cap) return 0;
+    if (m->d_buf) cudaFree(m->d_buf);
+    m->d_buf = nullptr; m->cap = 0;
+    CU_TRY(cudaMalloc(&m->d_buf, n * sizeof(long long)));
+    m->cap = n;
+    return 0;
+}
+}  // namespace
+
+int polar_b200_comm_unique_id(unsigned char* id128) {
+    if (!id128) return POLAR_B200_E_ARG;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return POLAR_B200_E_NONCCL;
+    ncclUniqueId id;
+    if (api.GetUniqueId(&id) != ncclSuccess) return POLAR_B200_E_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(id128, &id, 128);
+    return POLAR_B200_OK;
+}
+
+int polar_b200_comm_init_rank(polar_b200_comm** out, int device, int nranks, int rank, const unsigned char* id128) {
+    if (!out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return POLAR_B200_E_ARG;
+    *out = nullptr;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return POLAR_B200_E_NONCCL;
+    CU_TRY(cudaSetDevice(device));
+    polar_b200_comm* m = new (std::nothrow) polar_b200_comm;
+    if (!m) return POLAR_B200_E_ARG;
+    m->device = device; m->nranks = nranks; m->rank = rank;
+    ncclUniqueId id;
+    memcpy(&id, id128, 128);
+    if (api.CommInitRank(&m->comm, nranks, id, rank) != ncclSuccess) { delete m; return POLAR_B200_E_NCCL; }
+    cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { api.CommDestroy(m->comm); delete m; return (int)e; }
+    *out = m;
+    return POLAR_B200_OK;
+}
+
+int polar_b200_comm_init_all(polar_b200_comm** out, int ndev, const int* devices) {
+    if (!out || ndev < 1 || !devices) return POLAR_B200_E_ARG;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return POLAR_B200_E_NONCCL;
+    std::vector<ncclComm_t> comms((size_t)ndev);
+    if (api.CommInitAll(comms.data(), ndev, devices) != ncclSuccess) return POLAR_B200_E_NCCL;
+    for (int i = 0; i < ndev; ++i) {
+        polar_b200_comm* m = new (std::nothrow) polar_b200_comm;
+        if (!m) return POLAR_B200_E_ARG;
+        m->comm = comms[i]; m->device = devices[i]; m->nranks = ndev; m->rank = i;
+        CU_TRY(cudaSetDevice(devices[i]));
+        CU_TRY(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
+        out[i] = m;
+    }
+    return POLAR_B200_OK;
+}
+
+int polar_b200_comm_allreduce_i64(polar_b200_comm* m, long long* values, int n) {
+    return polar_b200_comm_allreduce_i64_group(&m, 1, &values, n);
+}
+
+// one call for all communicators this process owns (ncclGroupStart/End): values[i] is communicator i's host vector
+int polar_b200_comm_allreduce_i64_group(polar_b200_comm** ms, int ncomm, long long** values, int n) {
+    if (!ms || !values || ncomm < 1 || n < 1) return POLAR_B200_E_ARG;
+    const NcclApi& api = nccl_api();
+    if (!api.ok) return POLAR_B200_E_NONCCL;
+    for (int i = 0; i < ncomm; ++i) {
+        if (!ms[i] || !values[i]) return POLAR_B200_E_ARG;
+        CU_TRY(cudaSetDevice(ms[i]->device));
+        int rc = comm_buffer(ms[i], (size_t)n);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(ms[i]->d_buf, values[i], (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, ms[i]->st));
+    }
+    bool bad = api.GroupStart() != ncclSuccess;
+    for (int i = 0; i < ncomm && !bad; ++i)
+        bad = api.AllReduce(ms[i]->d_buf, ms[i]->d_buf, (size_t)n, ncclInt64, ncclSum, ms[i]->comm, ms[i]->st) != ncclSuccess;
+    if (api.GroupEnd() != ncclSuccess || bad) return POLAR_B200_E_NCCL;
+    for (int i = 0; i < ncomm; ++i) {
+        CU_TRY(cudaSetDevice(ms[i]->device));
+        CU_TRY(cudaMemcpyAsync(values[i], ms[i]->d_buf, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, ms[i]->st));
+        CU_TRY(cudaStreamSynchronize(ms[i]->st));
+    }
+    return POLAR_B200_OK;
+}
+
+int polar_b200_comm_destroy(polar_b200_comm* m) {
+    if (!m) return POLAR_B200_E_ARG;
+    cudaSetDevice(m->device);
+    if (m->comm && nccl_api().ok) nccl_api().CommDestroy(m->comm);
+    cudaFree(m->d_buf);
+    if (m->st) cudaStreamDestroy(m->st);
+    delete m;
     return POLAR_B200_OK;
 }
 

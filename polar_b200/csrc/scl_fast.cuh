@@ -128,8 +128,10 @@ struct Cfg {
     static constexpr __host__ __device__ int ss_rows() { int r = 0; for (int j = 1; j <= SWL; ++j) if (!s_global(j)) r += swords(j); return r; }
     static constexpr int GS_ROWS = gs_rows();
     static constexpr int SS_ROWS = ss_rows();
-    // + 64 bytes of clone scatter / free-path stack, + 128 bytes of decision-margin slots (one per codeword of the warp)
-    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64 + 128;
+    // + 64 bytes of clone scatter / free-path stack, + 16 bytes for the decision-margin slot of the one-codeword-per-warp
+    // kernels, which have no register to spare (the others keep the margin in a register; anything more per warp would
+    // cost the N = 2048 variants their fourth block per SM)
+    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64 + (WLOG_ == 5 ? 16 : 0);
     static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
     // lists <= 16 (G > 1 codewords per warp): the channel LLRs of the warp's codewords are staged TRANSPOSED
     // ([position / 4][codeword][4], so that a lane still reads float4) behind the XS arrays, which are stored
@@ -163,6 +165,7 @@ struct Warp {          // per-warp pointers
 
 struct Lane {          // per-path state
     uint32_t pm;       // path metric above the list's best, Q8.24 (q_of / q_add)
+    uint32_t mg;       // lists <= 16: smallest decision margin so far (Q8.24; plain SC: float bits of the smallest |LLR|)
     bool active;
     unsigned long long px;   // column pointers of LLR layers T.. (index lam - T)
     unsigned long long ps;   // column pointers of partial-sum word layers 1..SWL (index lam - 1)
@@ -222,8 +225,9 @@ __device__ __forceinline__ uint32_t q_add(uint32_t a, uint32_t b) { const uint32
 // Decision margin: the gap (>= 0) between the worst fork that was kept and the best fork that was dropped. A gap
 // below the arithmetic's own error means the double-precision reference may decide otherwise; such codewords are
 // re-decoded in double (strict mode). Only gaps below tauq are recorded (the smallest one per codeword).
-template <int W> __device__ __forceinline__ void note_gap(const Warp& w, uint32_t gapq, uint32_t tauq) {
-    if (gapq < tauq && (w.lane & (W - 1)) == 0) atomicMin(w.mg + w.g, gapq);
+template <int W> __device__ __forceinline__ void note_gap(const Warp& w, Lane& s, uint32_t gapq, uint32_t tauq) {
+    if constexpr (W == 32) { if (gapq < tauq && w.lane == 0) atomicMin(w.mg, gapq); }    // rare: only sub-threshold gaps
+    else s.mg = min(s.mg, gapq);                     // uniform over the lanes of a codeword
 }
 
 // ---- tensor memory as a per-warp scratch (tcgen05.ld/st, shape 32x32b: lane i of the warp <-> TMEM lane i of
@@ -919,7 +923,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
     if constexpr (W == 1) {
         // plain SC (list 1): the better of the two forks survives, fork 0 on a tie (index order, PolarCode.cpp:543-553),
         // i.e. the sign of the leaf LLR; no metric is kept at all (a single path needs none). Margin = |LLR|.
-        if (ax < tau) atomicMin(w.mg + w.g, q_of(ax));
+        s.mg = min(s.mg, __float_as_uint(ax));          // non-negative floats order like their bit patterns
         return neg ? 1u : 0u;
     }
     // both fork metrics from one log1p(exp(-|x|)) (softplus_ref(-|x|) and softplus_ref(+|x|)), as fixed-point increments
@@ -944,7 +948,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 const unsigned ka = gmax<W>(s.active ? klo : 0u);
                 if (kb > ka) {
                     if (s.active) s.pm = klo;
-                    note_gap<W>(w, kb - ka, tauq);
+                    note_gap<W>(w, s, kb - ka, tauq);
                     return like1 ? 1u : 0u;
                 }
             }
@@ -975,7 +979,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 keptA &= ~(1u << al);
                 kbl = kb; kal = ka;
             }
-            note_gap<W>(w, min(kbn, kal) - max(kan, kbl), tauq);     // best dropped fork - worst kept fork
+            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);  // best dropped fork - worst kept fork
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1012,7 +1016,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             }
         }
         if (2 * A > L) {
-            note_gap<W>(w, min(kbn, kal) - max(kan, kbl), tauq);
+            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);
             const bool ka_ = (keptA >> slot) & 1u, kb_ = (keptB >> slot) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1178,7 +1182,8 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         s.active = valid && (slot == c0);
         s.pm = 0u; s.px = 0; s.ps = 0; s.sreg = 0;
         w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
-        w.mg[lane] = kQSat;                             // smallest decision margin so far: none recorded
+        if constexpr (W == 32) { if (lane == 0) *w.mg = kQSat; }   // smallest decision margin so far: none recorded
+        s.mg = (W == 1) ? 0x7F800000u : kQSat;
         __syncwarp();
         int sp = L - 1;
         float lam_n = 0.0f;
@@ -1402,7 +1407,10 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         if (a.margin != nullptr || a.flag_list != nullptr) {
             // the final pick is a decision too: runner-up metric - winner's metric (0 when two paths tie, or when every
             // candidate is saturated and the reference's choice cannot be reproduced from these metrics)
-            uint32_t mgq = w.mg[w.g];
+            uint32_t mgq;
+            if constexpr (W == 32) mgq = *w.mg;
+            else if constexpr (W == 1) mgq = q_of(__uint_as_float(s.mg));
+            else mgq = s.mg;
             if constexpr (W > 1) {
                 const unsigned second = gmin<W>((eligible && slot != win) ? s.pm : 0xFFFFFFFFu);
                 if (cand == 0) mgq = 0u;
