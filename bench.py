@@ -335,13 +335,35 @@ def run_ours(args):
         off = (e - rank * B) % ns
         counts[0, e, 0] = int(be[off::ns].sum().item())
         counts[0, e, 1] = int(be[off::ns].numel())
-    t = torch.tensor([ms, e2e_s, ms_other, h2d_ms], dtype=torch.float64, device=dev)
+    # ---- the BLER workload end to end on the device (polar_b200_bler_sweep): synthesis, decode and comparison stay on
+    # the GPU, per step only (seed, index range) go in and the counters come out ----
+    sweep_steps = max(1, min(args.steps, args.e2e_steps))
+    sw_counts = code.bler_sweep_device(sweep, [L], B, SEED + 1, first_index=rank * B)       # warm
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(sweep_steps):
+        sw_counts = code.bler_sweep_device(sweep, [L], B, SEED + 1, first_index=(world * (i + 1) + rank) * B)
+    sweep_s = time.perf_counter() - t0
+    barrier()
+
+    t = torch.tensor([ms, e2e_s, ms_other, h2d_ms, sweep_s], dtype=torch.float64, device=dev)
     fl = torch.tensor([flagged, flagged_other, differs_between_modes], dtype=torch.int64, device=dev)
+    collective = "none (one GPU)"
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(fl, op=dist.ReduceOp.SUM)
-        counts = bler.all_reduce_counts(counts, dev)
-    ms, e2e_s, ms_other, h2d_ms = (float(x) for x in t.tolist())
+        # the path's one real collective -- the (num_err, num_run) counters -- goes through the library's own NCCL
+        # communicator (polar_b200_comm_*: ncclAllReduce issued from C++); torch.distributed only carries the 128-byte id
+        def exchange(b):
+            tt = torch.tensor(list(b), dtype=torch.uint8, device=dev)
+            dist.broadcast(tt, 0)
+            return bytes(tt.cpu().tolist())
+        comm = bler.Comm(local, world, rank, exchange)
+        counts = comm.all_reduce(counts)
+        sw_counts = comm.all_reduce(sw_counts)
+        comm.close()
+        collective = "ncclAllReduce(int64 x %d) from C++ (polar_b200_comm_allreduce_i64), ranks = %d" % (counts.size, world)
+    ms, e2e_s, ms_other, h2d_ms, sweep_s = (float(x) for x in t.tolist())
     flagged, flagged_other, differs_between_modes = (int(x) for x in fl.tolist())
 
     if rank == 0:
@@ -381,6 +403,12 @@ def run_ours(args):
                     "pipelined_chunks": code.info(7), "mode": mode,
                     "h2d_copy_gbs_per_gpu_all_ranks_at_once": B * N * 4 / (h2d_ms * 1e-3) / 1e9,
                     "h2d_needed_gbs_per_gpu_at_device_rate": B * N * 4 / (ms_step * 1e-3) / 1e9},
+            "e2e_sweep": {"value": world * B * sweep_steps / sweep_s, "unit": "codewords/s",
+                          "what": "polar_b200_bler_sweep: Philox info bits + encoder + AWGN (double) + decode + block-error count on "
+                                  "the device, fresh codewords every step; per step only the index range goes in and the counters come out",
+                          "h2d_bytes_per_step": 8 * len(sweep) + 64, "d2h_bytes_per_step": 16 * len(sweep), "steps": sweep_steps,
+                          "bler_last_step": float(sw_counts[0, :, 0].sum() / max(1, sw_counts[0, :, 1].sum())),
+                          "collective": collective},
             "gpu_launches": int(launches),
             # informational, beside the contract's HBM roofline: the decoder is bound by instruction issue, so the same
             # rate is also stated against the issue-slot ceiling (148 SMs x 4 schedulers x SM clock), with the warp

@@ -942,7 +942,7 @@ int ensure_flags(polar_b200_ctx* c, int B) {
     if (B > c->flag_cap) {
         if (c->d_flag_list) cudaFree(c->d_flag_list);
         c->d_flag_list = nullptr; c->flag_cap = 0;
-        CU_TRY(cudaMalloc(&c->d_flag_list, (size_t)B * sizeof(int)));
+        CU_TRY(cudaMalloc(&c->d_flag_list, 2 * (size_t)B * sizeof(int)));     // second half: the third pass's list
         c->flag_cap = B;
     }
     return 0;
@@ -952,7 +952,8 @@ int ensure_flags(polar_b200_ctx* c, int B) {
 constexpr int kMaxNExact = 13;
 template <class In>
 int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, cudaStream_t st,
-                 const int* list = nullptr, const int* count = nullptr, const CountSpec* cs = nullptr) {
+                 const int* list = nullptr, const int* count = nullptr, const CountSpec* cs = nullptr,
+                 int* list2 = nullptr, int* count2 = nullptr) {
     const int n = c->n, N = c->N;
     exact::Args<In> a;
     memset(&a, 0, sizeof(a));
@@ -963,7 +964,7 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     int off = 0;
     for (int lam = 0; lam <= n - 1; ++lam) { a.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }
     a.smem_s_rows = off;
-    const int fixed = a.smem_s_rows * 128 + 2 * 16 * 32 + 32 + 16;
+    const int fixed = a.smem_s_rows * 128 + 2 * 16 * 32 + 48 + (int)sizeof(exact::Tables) + 16;
     int lamS = n;                                    // smallest footprint, then grow while it fits
     while (lamS > 1) {
         const int xr = (1 << (n - (lamS - 1) + 1)) - 2;
@@ -985,7 +986,7 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
         CU_TRY(cudaMalloc(&c->d_ex_gx, need));
         c->ex_gx_bytes = need;
     }
-    a.llr = llr; a.out = out; a.list = list; a.count = count;
+    a.llr = llr; a.out = out; a.list = list; a.count = count; a.list2 = list2; a.count2 = count2;
     a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
     a.gx = c->d_ex_gx;
     a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
@@ -993,6 +994,8 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
     int W = 1; while (W < L) W <<= 1;
     a.W = W;
+    a.big = env_int("POLAR_B200_EXACT_BIG", 64);
+    if (a.big < 32) a.big = 32;
     CU_TRY(cudaFuncSetAttribute(exact::scl_exact_kernel<In>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     exact::scl_exact_kernel<In><<<blocks, exact::NT, smem, st>>>(a);
     CU_TRY(cudaGetLastError());
@@ -1004,8 +1007,17 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
 // STRICT mode's second pass over the flagged codewords
 int redecode_flagged(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, cudaStream_t st,
                      const CountSpec* cs = nullptr) {
-    if (c->n <= kMaxNExact && L <= 32 && (cs || env_int("POLAR_B200_REDECODE_GENERIC", 0) == 0))
-        return decode_exact<float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count, cs);
+    if (c->n <= kMaxNExact && L <= 32 && (cs || env_int("POLAR_B200_REDECODE_GENERIC", 0) == 0)) {
+        if (cs) return decode_exact<float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count, cs);
+        // second pass: double with short dependency chains; third pass (normally empty): whatever the second pass found
+        // to hinge on an exact cancellation, with the reference's literal formulas
+        int* list2 = c->d_flag_list + c->flag_cap;
+        int* count2 = c->d_flag_count + 1;
+        CU_TRY(cudaMemsetAsync(count2, 0, sizeof(int), st));
+        int rc = decode_exact<float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count, nullptr, list2, count2);
+        if (rc) return rc;
+        return decode_generic<double, float>(c, llr, B, L, out, st, list2, count2);
+    }
     return decode_generic<double, float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count);
 }
 

@@ -26,12 +26,80 @@ namespace exact {
 
 constexpr int NT = 256;          // threads per block
 
+// ---- double-precision check node and metric update with short dependency chains ----
+// The reference's literal formulas cost three exp, a division and a log per check node with CUDA's general-purpose
+// double routines: about 70 dependent double operations, and one decode is one long chain of them. What the second
+// pass has to deliver is the reference's DECISIONS, i.e. the same real-valued functions to far better than the margins
+// that matter (strict mode hands it decisions closer than ~1e-5; it is accurate to ~1e-15), so it evaluates
+//     f(a, b)      = sign * min + log1p(e^-|a+b|) - log1p(e^-|a-b|)      (== log((e^(a+b) + 1) / (e^a + e^b)), :438-441)
+//     softplus(x)  = max(x, 0) + log1p(e^-|x|)                           (== log(1 + e^x), :483, :505-506)
+// with table-driven kernels: e^-s = 2^(k/64) * 2^(k div 64) * p5(r), log1p(e) = -log(c_j) + p6((1 + e) c_j - 1), about 20
+// dependent operations per check node. Codewords that take a decision on a double-precision margin below 1e-9 (exact
+// cancellations, whose outcome in the reference is decided by the last-bit rounding of its literal formulas) are passed
+// on to the literal-formula kernel (list2).
+struct Tables {
+    double exp2j[64];        // 2^(j/64)
+    double rcp[132];         // c_j = 1 / (1 + (j + 1/2) / 128)
+    double mlog[132];        // -log(c_j)
+};
+__device__ __forceinline__ void build_tables(Tables* t, int tid, int nt) {
+    for (int j = tid; j < 64; j += nt) t->exp2j[j] = exp2((double)j / 64.0);
+    for (int j = tid; j < 129; j += nt) {
+        const double c = 1.0 / (1.0 + ((double)j + 0.5) / 128.0);
+        t->rcp[j] = c;
+        t->mlog[j] = -log(c);
+    }
+}
+// e^-s for s >= 0
+__device__ __forceinline__ double exp_neg(double s, const Tables* t) {
+    s = fmin(s, 700.0);                                     // e^-700 ~ 1e-304: below anything that matters, still normal
+    const double kd = rint(s * -92.33248261689366);         // -s * 64 / ln 2
+    double r = fma(kd, -0.010830424667801708, -s);          // -s - k ln2/64, ln2/64 split in two parts
+    r = fma(kd, -2.8447437476627285e-11, r);
+    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);             // |r| <= ln2/128: r^6/720 < 4e-17
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kd;
+    const double v = t->exp2j[k & 63] * p;                  // in [1, 2.02)
+    return __hiloint2double(__double2hiint(v) + ((k >> 6) << 20), __double2loint(v));   // * 2^(k div 64)
+}
+// log(1 + e) for 0 <= e <= 1
+__device__ __forceinline__ double log1p_unit(double e, const Tables* t) {
+    const double m = 1.0 + e;
+    const int j = (int)((m - 1.0) * 128.0);                 // 0 .. 128
+    const double r = fma(m, t->rcp[j], -1.0);               // |r| <= 2^-8: r^7/7 < 2e-18
+    double q = fma(r, -1.0 / 6.0, 1.0 / 5.0);
+    q = fma(q, r, -0.25);
+    q = fma(q, r, 1.0 / 3.0);
+    q = fma(q, r, -0.5);
+    q = fma(q * r, r, r);
+    return t->mlog[j] + q;
+}
+__device__ __forceinline__ double f_fast(double a, double b, const Tables* t) {
+    const double ma = fabs(a), mb = fabs(b);
+    const double sa = (a < 0) ? -1.0 : (double)(a > 0), sb = (b < 0) ? -1.0 : (double)(b > 0);
+    double y = sa * sb * fmin(ma, mb);
+    if (40.0 > fmax(ma, mb))                                // PolarCode.cpp:438: exact box-plus below 40, sign-min otherwise
+        y += log1p_unit(exp_neg(fabs(a + b), t), t) - log1p_unit(exp_neg(fabs(a - b), t), t);
+    return y;
+}
+__device__ __forceinline__ double softplus_fast(double x, const Tables* t) {
+    if (x > 709.782712893384) return CUDART_INF;            // exp(x) overflows a double (:483 yields +inf)
+    if (x < -36.7368005696771) return 0.0;                  // 1 + exp(x) rounds to 1
+    return fmax(x, 0.0) + log1p_unit(exp_neg(fabs(x), t), t);
+}
+constexpr double kTieMargin = 1e-9;
+
 template <class In>
 struct Args {
     const In* llr;               // [B][N], converted to double on load
     uint32_t* out;               // [B][KW]
     const int* list;             // null, or the codeword indices to decode
     const int* count;            // with `list`: number of entries (device memory)
+    int* list2;                  // null, or: codewords decided on a double-precision margin below kTieMargin are appended
+    int* count2;                 //   here (to be decoded once more with the literal formulas) and are neither stored nor counted
     const uint32_t* frozen_words;
     const uint16_t* info_order;
     const uint32_t* crc_masks;
@@ -40,6 +108,7 @@ struct Args {
     int B, n, K, crc, L;
     int W;                       // list size rounded up to a power of two (work is spread over W paths x beta)
     int lamS;                    // first layer kept in shared memory
+    int big;                     // layers with more than this many (path, beta) items are refreshed by the whole block
     int smem_x_rows, smem_s_rows;
     int s_off[kMaxN + 2];        // word-row offset of partial-sum layer lam (all of them in shared memory)
     // fused block-error counting, as in fast::Args
@@ -66,6 +135,8 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
     unsigned char* ps = px + 16 * 32;                                                        // [16][32] partial-sum pointers
     unsigned char* srcof = ps + 16 * 32;                                                     // [32] clone scatter
     volatile uint32_t* actp = reinterpret_cast<volatile uint32_t*>(srcof + 32);              // active-path mask
+    Tables* tb = reinterpret_cast<Tables*>(srcof + 48);
+    build_tables(tb, tid, NT);
     double* gx = a.gx + a.gx_stride * blockIdx.x;
 
     auto xrow = [&](int lam, int beta) -> double* {
@@ -85,6 +156,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
         uint32_t s_n = 0;
         int stk = slot, sp = L - 1;
         double lam_n = 0;
+        double dmin = CUDART_INF;                          // smallest decision margin (warp-uniform)
         uint32_t frozen_word = 0;
         __syncthreads();                                   // the previous codeword's output gather is done
         for (int i = tid; i < 2 * 16 * 32; i += NT) px[i] = 0;          // px and ps
@@ -117,7 +189,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                     else bit = (srow(lam, beta >> 5)[ps[(lam - 1) * 32 + path]] >> (beta & 31)) & 1u;
                     y = x1 + (bit ? -x0 : x0);                                 // PolarCode.cpp:448-451
                 } else {
-                    y = Arith<double>::f(x0, x1);                              // PolarCode.cpp:438-446
+                    y = f_fast(x0, x1, tb);                                    // PolarCode.cpp:438-446
                 }
                 if (lam == n) lam_n = y; else xrow(lam, beta)[path] = y;
             }
@@ -126,10 +198,10 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
         for (int phi = 0; phi < N; ++phi) {
             // ---- refresh LLR layers lam_top..n (PolarCode.cpp:422-455): big layers by the block, small ones by warp 0 ----
             const int lam_top = (phi == 0) ? 1 : n - (__ffs(phi) - 1);
-            const bool any_big = ((1 << (n - lam_top)) << wsh) > 32;
+            const bool any_big = ((1 << (n - lam_top)) << wsh) > a.big;
             if (any_big) __syncthreads();                  // warp 0's decisions of the leaves before this one are visible
             for (int lam = lam_top; lam <= n; ++lam) {
-                const bool big = ((1 << (n - lam)) << wsh) > 32;
+                const bool big = ((1 << (n - lam)) << wsh) > a.big;
                 const bool is_g = (lam == lam_top) && (phi != 0);
                 if (big) {
                     refresh(lam, is_g, tid, NT);
@@ -148,11 +220,16 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
             const bool frozen = (frozen_word >> (phi & 31)) & 1u;
             uint32_t u = 0;
             if (frozen) {
-                if (active) pm += Arith<double>::softplus(-lam_n);             // PolarCode.cpp:475-487
+                if (active) pm += softplus_fast(-lam_n, tb);                   // PolarCode.cpp:475-487
             } else {
                 // PolarCode.cpp:489-607. Metrics are kept positive (m = -probForks).
-                const double m0 = pm + Arith<double>::softplus(-lam_n);
-                const double m1 = pm + Arith<double>::softplus(lam_n);
+                // both fork metrics share log1p(e^-|x|): softplus(-x) and softplus(x) differ by max(-+x, 0)
+                const double al = fabs(lam_n);
+                double lo = 0.0, hi = CUDART_INF;                              // likely / unlikely increment (:505-506)
+                if (!(al > 36.7368005696771)) lo = log1p_unit(exp_neg(al, tb), tb);
+                if (!(al > 709.782712893384)) hi = al + lo;
+                const double m0 = pm + (lam_n < 0 ? hi : lo);
+                const double m1 = pm + (lam_n < 0 ? lo : hi);
                 const unsigned act_g = __ballot_sync(FULL_MASK, active) & gmask_lo;
                 const int A = __popc(act_g);
                 bool keep0 = active, keep1 = active;
@@ -163,6 +240,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                     const double worst_likely = group_max<double>(active ? lo : -CUDART_INF, 32);
                     const double best_unlikely = group_min<double>(active ? hi : CUDART_INF, 32);
                     if (best_unlikely > worst_likely) {
+                        dmin = fmin(dmin, best_unlikely - worst_likely);
                         slow = false;
                         keep0 = active && (m0 <= m1);    // m0 == m1 cannot happen here (would not be strict)
                         keep1 = active && !keep0;
@@ -184,6 +262,11 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                     }
                     keep0 = active && r0 < L;
                     keep1 = active && r1 < L;
+                    // margin of this selection: best dropped fork - worst kept fork
+                    const double kept = group_max<double>(rmax<double>(keep0 ? m0 : -CUDART_INF, keep1 ? m1 : -CUDART_INF), 32);
+                    const double dropped = group_min<double>(rmin<double>((active && !keep0) ? m0 : CUDART_INF,
+                                                                          (active && !keep1) ? m1 : CUDART_INF), 32);
+                    dmin = fmin(dmin, dropped - kept);
                 }
                 const bool kill = active && !keep0 && !keep1;
                 const bool clone = keep0 && keep1;
@@ -295,7 +378,14 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
             const unsigned cand = __ballot_sync(FULL_MASK, eligible && pm == best);
             const int win = cand ? (__ffs(cand) - 1) : 0;
             const bool wa = (act_all >> win) & 1u;
+            const double second = group_min<double>((eligible && lane != win) ? pm : CUDART_INF, 32);
+            if (cand != 0) dmin = fmin(dmin, second - best);
             __syncwarp();
+            if (a.list2 != nullptr && dmin < kTieMargin) {
+                // an exact cancellation somewhere: only the literal formulas resolve it the way the reference does
+                if (lane == 0) a.list2[atomicAdd(a.count2, 1)] = cw;
+                continue;
+            }
             // ---- output gather: decoded[j] = u-hat[order[j]], PolarCode.cpp:171-174 ----
             const uint32_t* U = srow(0, 0) + win;
             bool differs = false;

@@ -445,6 +445,7 @@ def test_device_front_end_matches_reference_encoder_and_channel(torch_cuda):
         assert torch.equal(llr2, llr[150:250]) and torch.equal(truth2, truth[150:250])
         # (c) noise statistics at 2 dB: z = (llr / (-4a) - a s) / sqrt(1/2)
         llr3, truth3 = pc.synthesize(2000, [2.0], seed=7)
+        assert llr3.abs().max().item() < 60.0
         info3 = unpack_bits(truth3.cpu().numpy().view(np.uint32), K)
         s = 2.0 * port.encode(info3[:200]).astype(np.float64) - 1.0
         a = 10.0 ** (2.0 / 20.0) * np.sqrt(K / N)
@@ -454,6 +455,57 @@ def test_device_front_end_matches_reference_encoder_and_channel(torch_cuda):
         llr4, truth4 = pc.synthesize(512, [4.0], seed=9)
         out = pc.decode_device(llr4, 8)
         assert int((out != truth4).any(dim=1).sum().item()) <= 2
+
+
+def test_fused_sweep_counts_equal_separate_decode_and_count(torch_cuda):
+    """polar_b200_bler_sweep (synthesis + decode with the block-error count fused into the kernels' tails, strict mode's
+    second pass counting what it re-decodes) against the same codewords synthesised, decoded and counted by separate
+    calls: the counters must be identical, in every arithmetic mode, for any chunking and any split of the index range."""
+    torch = torch_cuda
+    from polar_b200 import PolarCode
+    for (n, K, crc, lists, count) in [(9, 256, 16, [1, 4, 32], 3000), (11, 1024, 16, [2, 32], 700), (7, 64, 8, [8], 999)]:
+        pc = PolarCode(n, K, 0.32, crc)
+        ebno = [1.0, 1.5, 2.5]
+        for mode in ("fp32", "strict"):
+            got = pc.bler_sweep_device(ebno, lists, count, seed=77, first_index=40, mode=mode)
+            llr, truth = pc.synthesize(count, ebno, 77, first_index=40)
+            want = np.zeros_like(got)
+            idx = (np.arange(count) + 40) % len(ebno)
+            for il, L in enumerate(lists):
+                err = (pc.decode_device(llr, L, mode=mode) != truth).any(dim=1).cpu().numpy()
+                for ie in range(len(ebno)):
+                    want[il, ie] = (int(err[idx == ie].sum()), int((idx == ie).sum()))
+            assert np.array_equal(got, want), (n, mode, got.tolist(), want.tolist())
+        # shards add up: [40, 40+count) = [40, 1040) + [1040, 40+count) for count > 1000
+        if count > 1000:
+            a = pc.bler_sweep_device(ebno, lists, 1000, seed=77, first_index=40, mode="strict")
+            b = pc.bler_sweep_device(ebno, lists, count - 1000, seed=77, first_index=1040, mode="strict")
+            assert np.array_equal(a + b, got)
+
+
+def test_cpp_multi_gpu_sweep_and_nccl_counters(torch_cuda):
+    """PolarCode::bler_sweep (C++): shards over the visible devices, one host thread each, counters summed with
+    ncclAllReduce through polar_b200_comm_*. With one device the communicator has one rank; with two or more the
+    result must equal the single-device sweep of the same index range (integer sums are order independent)."""
+    torch = torch_cuda
+    from polar_b200 import PolarCode, _lib
+    pc = PolarCode(9, 256, 0.32, 16)
+    ebno, lists, total = [1.0, 2.0], [1, 8], 4096
+    one = pc.bler_sweep_device(ebno, lists, total, seed=5, first_index=0)
+    bler1, c1 = pc.bler_sweep(ebno, lists, total, seed=5, devices=[0])
+    assert np.array_equal(c1, one) and np.all(c1[..., 1] == total // 2)
+    nd = _lib.dev().polar_b200_device_count()
+    assert nd == torch.cuda.device_count()
+    if nd >= 2:
+        bler2, c2 = pc.bler_sweep(ebno, lists, total, seed=5)
+        assert np.array_equal(c2, one)
+    # the communicator on its own: one rank, identity
+    import ctypes as C
+    from polar_b200 import bler
+    comm = bler.Comm(0, 1, 0, lambda b: b)
+    v = np.arange(6, dtype=np.int64).reshape(1, 3, 2)
+    assert np.array_equal(comm.all_reduce(v), v)
+    comm.close()
 
 
 def test_device_bler_sweep_agrees_with_host_sweep(torch_cuda):
