@@ -957,7 +957,7 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     const int n = c->n, N = c->N;
     exact::Args<In> a;
     memset(&a, 0, sizeof(a));
-    int bps = env_int("POLAR_B200_EXACT_BPS", 1);
+    int bps = env_int("POLAR_B200_EXACT_BPS", 3);
     if (bps < 1) bps = 1;
     if (bps > 4) bps = 4;
     const int budget = (220 * 1024) / bps;
@@ -994,10 +994,14 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
     int W = 1; while (W < L) W <<= 1;
     a.W = W;
-    a.big = env_int("POLAR_B200_EXACT_BIG", 64);
+    a.big = env_int("POLAR_B200_EXACT_BIG", 32);
     if (a.big < 32) a.big = 32;
     CU_TRY(cudaFuncSetAttribute(exact::scl_exact_kernel<In>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    exact::scl_exact_kernel<In><<<blocks, exact::NT, smem, st>>>(a);
+    int nt = env_int("POLAR_B200_EXACT_THREADS", exact::NT);
+    if (nt < 32) nt = 32;
+    if (nt > exact::NT) nt = exact::NT;
+    nt &= ~31;
+    exact::scl_exact_kernel<In><<<blocks, nt, smem, st>>>(a);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     if (!list) { c->last_wpb = exact::NT / 32; c->last_blocks = blocks; c->last_smem = smem; c->last_kernel = -5; }

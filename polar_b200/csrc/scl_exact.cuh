@@ -24,7 +24,7 @@
 
 namespace exact {
 
-constexpr int NT = 256;          // threads per block
+constexpr int NT = 256;          // threads per block at most (the launch may use fewer: blockDim.x)
 
 // ---- double-precision check node and metric update with short dependency chains ----
 // The reference's literal formulas cost three exp, a division and a log per check node with CUDA's general-purpose
@@ -121,7 +121,7 @@ struct Args {
 template <class In>
 __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nt = blockDim.x;
     const int n = a.n, N = 1 << n, L = a.L, W = a.W, lamS = a.lamS;
     int wsh = 0;
     while ((1 << wsh) < W) ++wsh;
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
     unsigned char* srcof = ps + 16 * 32;                                                     // [32] clone scatter
     volatile uint32_t* actp = reinterpret_cast<volatile uint32_t*>(srcof + 32);              // active-path mask
     Tables* tb = reinterpret_cast<Tables*>(srcof + 48);
-    build_tables(tb, tid, NT);
+    build_tables(tb, tid, nt);
     double* gx = a.gx + a.gx_stride * blockIdx.x;
 
     auto xrow = [&](int lam, int beta) -> double* {
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
         double dmin = CUDART_INF;                          // smallest decision margin (warp-uniform)
         uint32_t frozen_word = 0;
         __syncthreads();                                   // the previous codeword's output gather is done
-        for (int i = tid; i < 2 * 16 * 32; i += NT) px[i] = 0;          // px and ps
+        for (int i = tid; i < 2 * 16 * 32; i += nt) px[i] = 0;          // px and ps
         if (tid == 0) *actp = 1u << (L - 1);
         __syncthreads();
 
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                 const bool big = ((1 << (n - lam)) << wsh) > a.big;
                 const bool is_g = (lam == lam_top) && (phi != 0);
                 if (big) {
-                    refresh(lam, is_g, tid, NT);
+                    refresh(lam, is_g, tid, nt);
                     if (lam < n && tid < 32) px[(lam - 1) * 32 + tid] = (unsigned char)tid;
                     __syncthreads();
                 } else if (wib == 0) {
