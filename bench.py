@@ -251,16 +251,25 @@ def run_ours(args):
     n, K, crc, L, sweep, _ = CONFIGS[args.config]
     N, B = 1 << n, args.batch
     mode = args.mode                                  # arithmetic of the headline arm (default: strict)
-    other = "fp32" if mode != "fp32" else "strict"
+    other = "fp32" if mode in ("strict", "f64") else "strict"
     code = PolarCode(n, K, 0.32, crc, device=local, mode=mode)
     KW = code.KW
 
     # this rank's shard of the global batch (weak scaling: B codewords per GPU), pinned on the host
-    h_llr = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
+    host_buf = None
+    if args.host_alloc == "wc":
+        # write-combined page-locked input buffer from the library (polar_b200_host_alloc): read by the GPU without
+        # snooping the CPU caches
+        from polar_b200 import HostBuffer
+        host_buf = HostBuffer((B, N), np.float32, write_combined=True)
+        h_llr = torch.from_numpy(host_buf.array)
+    else:
+        h_llr = torch.empty((B, N), dtype=torch.float32, pin_memory=True)
     h_out = torch.empty((B, KW), dtype=torch.int32, pin_memory=True)
     info, _ = synth.make_shard(code, SEED, rank * B, B, sweep=sweep, out_llr=h_llr.numpy())
     d_truth = torch.from_numpy(pack_bits(info).view(np.int32)).to(dev)
-    d_llr = h_llr.to(dev)
+    d_llr = torch.empty((B, N), dtype=torch.float32, device=dev)
+    d_llr.copy_(h_llr)
     d_out = torch.empty((B, KW), dtype=torch.int32, device=dev)
     d_out2 = torch.empty((B, KW), dtype=torch.int32, device=dev)
     d_berr = torch.zeros(B, dtype=torch.uint8, device=dev)
@@ -330,11 +339,13 @@ def run_ours(args):
     # per-Eb/N0 block-error counters of this rank's shard; global codeword index g uses sweep[g % len(sweep)]
     ns = len(sweep)
     be = d_berr.to(torch.int64)
-    counts = np.zeros((1, ns, 2), np.int64)
+    be2 = (d_out2 != d_truth).any(dim=1).to(torch.int64)
+    counts = np.zeros((2, ns, 2), np.int64)          # [headline mode, other mode][Eb/N0 point][num_err, num_run]
     for e in range(ns):
         off = (e - rank * B) % ns
         counts[0, e, 0] = int(be[off::ns].sum().item())
-        counts[0, e, 1] = int(be[off::ns].numel())
+        counts[1, e, 0] = int(be2[off::ns].sum().item())
+        counts[:, e, 1] = int(be[off::ns].numel())
     # ---- the BLER workload end to end on the device (polar_b200_bler_sweep): synthesis, decode and comparison stay on
     # the GPU, per step only (seed, index range) go in and the counters come out ----
     sweep_steps = max(1, min(args.steps, args.e2e_steps))
@@ -378,12 +389,15 @@ def run_ours(args):
         out = {
             "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if mode == "fp32" else ("f64" if mode == "f64" else "f32+f64"),
+            "vs_baseline": None, "dtype": "f32" if mode in ("fp32", "minsum") else ("f64" if mode == "f64" else "f32+f64"),
             "data": "synthetic",
             "config": {"workload": workload_name(args.config, B), "global_batch": world * B,
                        "arithmetic": {"strict": "fp32 kernels; codewords decided on a margin below tau decoded again in double "
                                                 "(bit-exact against the double reference, see `parity`)",
-                                      "fp32": "fp32 kernels alone", "f64": "everything in double"}[mode],
+                                      "fp32": "fp32 kernels alone", "f64": "everything in double",
+                                      "minsum": "OPT-IN, NOT THE REFERENCE'S ARITHMETIC: min-sum check nodes + hardware-friendly "
+                                                "metric update (SURVEY.md section 8(f)4); compare `modes` and the per-point BLER "
+                                                "of both modes"}[mode],
                        "l2": "input %d MiB per GPU per step > 126 MB L2, no flush needed" % (B * N * 4 >> 20)
                              if B * N * 4 > 126e6 else "input %d MiB per GPU per step fits L2 (small plumbing config)" % (B * N * 4 >> 20),
                        "sharding": "contiguous codeword blocks per rank, no data-path collective; counters all-reduced"},
@@ -400,7 +414,7 @@ def run_ours(args):
                       "codewords_differing_between_modes": differs_between_modes},
             "e2e": {"value": world * B * e2e_steps / e2e_s, "unit": "codewords/s", "h2d_bytes_per_step": B * N * 4,
                     "d2h_bytes_per_step": B * KW * 4, "steps": e2e_steps, "matches_device_arm": e2e_ok,
-                    "pipelined_chunks": code.info(7), "mode": mode,
+                    "pipelined_chunks": code.info(7), "mode": mode, "host_buffer": args.host_alloc,
                     "h2d_copy_gbs_per_gpu_all_ranks_at_once": B * N * 4 / (h2d_ms * 1e-3) / 1e9,
                     "h2d_needed_gbs_per_gpu_at_device_rate": B * N * 4 / (ms_step * 1e-3) / 1e9},
             "e2e_sweep": {"value": world * B * sweep_steps / sweep_s, "unit": "codewords/s",
@@ -417,7 +431,8 @@ def run_ours(args):
             "clocks": clocks,
         }
         per_point = [{"ebno_db": float(sweep[e]), "n": int(counts[0, e, 1]), "err_gpu": int(counts[0, e, 0]),
-                      "bler_gpu": float(counts[0, e, 0] / counts[0, e, 1]), "ci95": wilson(int(counts[0, e, 0]), int(counts[0, e, 1]))}
+                      "bler_gpu": float(counts[0, e, 0] / counts[0, e, 1]), "ci95": wilson(int(counts[0, e, 0]), int(counts[0, e, 1])),
+                      "err_gpu_%s_mode" % other: int(counts[1, e, 0])}
                      for e in range(ns)]
         out["bler"] = float(counts[0, :, 0].sum() / counts[0, :, 1].sum())
         if world == 1 and not args.no_cpu:
@@ -456,9 +471,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c4", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=None, help="codewords per GPU per step (default 65536; 4096 for c1)")
-    ap.add_argument("--mode", default=os.environ.get("POLAR_B200_MODE", "strict"), choices=["strict", "fp32", "f64"],
+    ap.add_argument("--mode", default=os.environ.get("POLAR_B200_MODE", "strict"), choices=["strict", "fp32", "f64", "minsum"],
                     help="arithmetic of the headline arm (the other of strict / fp32 is reported in `modes`)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--host-alloc", default="pinned", choices=["pinned", "wc"],
+                    help="host LLR buffer of the end-to-end arm: torch pinned memory, or write-combined from the library")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

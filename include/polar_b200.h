@@ -76,6 +76,14 @@ const char* polar_b200_strerror(int code);
 /* Words of packed output per codeword: ceil(K/32). */
 int polar_b200_info_words(int K);
 
+/*
+ * Page-locked host memory for the *_host entry points (plain malloc'ed memory works too, the copies are then staged by
+ * the driver). write_combined != 0: not cached by the CPU -- fast to fill sequentially and to read from the device over
+ * PCIe (no snooping), very slow to read back on the CPU: for LLR input buffers only. NULL on failure.
+ */
+void* polar_b200_host_alloc(size_t bytes, int write_combined);
+int polar_b200_host_free(void* p);
+
 /* CUDA devices visible to this process (0 when there is none). */
 int polar_b200_device_count(void);
 

@@ -39,6 +39,25 @@ def pack_bits(bits):
 MODES = {"fp32": 0, "strict": 1, "f64": 2, "minsum": 3}
 
 
+class HostBuffer:
+    """Page-locked host memory from the library (polar_b200_host_alloc), exposed as a numpy array `.array`.
+    write_combined=True is meant for LLR input buffers: filled once by the CPU, read by the GPU over PCIe."""
+
+    def __init__(self, shape, dtype=np.float32, write_combined=False):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = _lib.dev().polar_b200_host_alloc(self.nbytes, 1 if write_combined else 0)
+        if not self.ptr:
+            raise _lib.PolarB200Error("polar_b200_host_alloc(%d bytes) failed" % self.nbytes)
+        buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            _lib.dev().polar_b200_host_free(self.ptr)
+            self.ptr = None
+
+
 class PolarCode:
     def __init__(self, n, K, epsilon=0.32, crc=0, reseed=True, device=0, mode=None):
         """n = log2(block length) as in the C++ reference (PolarCode.h:19). reseed=True calls

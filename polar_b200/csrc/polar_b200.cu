@@ -1263,6 +1263,17 @@ const char* polar_b200_strerror(int code) {
 
 int polar_b200_info_words(int K) { return (K + 31) / 32; }
 
+void* polar_b200_host_alloc(size_t bytes, int write_combined) {
+    void* p = nullptr;
+    const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    if (bytes == 0 || cudaHostAlloc(&p, bytes, flags) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+int polar_b200_host_free(void* p) {
+    if (!p) return POLAR_B200_E_ARG;
+    return (int)cudaFreeHost(p);
+}
+
 int polar_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

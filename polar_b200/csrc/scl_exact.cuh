@@ -79,8 +79,9 @@ __device__ __forceinline__ double log1p_unit(double e, const Tables* t) {
 }
 __device__ __forceinline__ double f_fast(double a, double b, const Tables* t) {
     const double ma = fabs(a), mb = fabs(b);
-    const double sa = (a < 0) ? -1.0 : (double)(a > 0), sb = (b < 0) ? -1.0 : (double)(b > 0);
-    double y = sa * sb * fmin(ma, mb);
+    const double mn = fmin(ma, mb);
+    // sgn(a) sgn(b) min(|a|, |b|) with sgn(0) = 0 (the minimum is then 0 anyway): sign bits XORed onto the minimum
+    double y = __hiloint2double(__double2hiint(mn) | ((__double2hiint(a) ^ __double2hiint(b)) & (int)0x80000000), __double2loint(mn));
     if (40.0 > fmax(ma, mb))                                // PolarCode.cpp:438: exact box-plus below 40, sign-min otherwise
         y += log1p_unit(exp_neg(fabs(a + b), t), t) - log1p_unit(exp_neg(fabs(a - b), t), t);
     return y;
@@ -163,35 +164,47 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
         if (tid == 0) *actp = 1u << (L - 1);
         __syncthreads();
 
-        // one tree layer for every active path: items (path, i), spread over the threads t0, t0 + T, ...
+        // one tree layer for every active path: items (path, i), spread over the threads t0, t0 + T, ... (T a multiple of W):
+        // a thread keeps its path and strides over i, so everything that depends on the path alone is hoisted
         auto refresh = [&](int lam, bool is_g, int t0, int T) {
             const int M = 1 << (n - lam);
-            const int total = M << wsh;
-            const uint32_t act = *actp;
-            for (int idx = t0; idx < total; idx += T) {
-                const int path = idx & (W - 1), i = idx >> wsh;
-                if (!((act >> path) & 1u)) continue;
+            const int path = t0 & (W - 1), i0 = t0 >> wsh, di = T >> wsh;
+            if (i0 >= M || !((*actp >> path) & 1u)) return;
+            const uint32_t* sw = (is_g && lam < n) ? srow(lam, 0) + ps[(lam - 1) * 32 + path] : nullptr;
+            if (lam == n) {
+                // the decision LLR (one item per path; warp 0, lane = path)
                 double x0, x1;
-                int beta = i;
-                if (lam == 1) {
-                    // channel layer: reference pairs are (2k, 2k+1); the result lands at the bit-reversed position
-                    x0 = (double)chan[2 * i]; x1 = (double)chan[2 * i + 1];
-                    beta = (n > 1) ? (int)(__brev((unsigned)i) >> (33 - n)) : 0;
-                } else {
+                if (n > 1) {
                     const double* src = xrow(lam - 1, 0) + px[(lam - 2) * 32 + path];
-                    x0 = src[(size_t)i << 5];
-                    x1 = src[(size_t)(i + M) << 5];
-                }
-                double y;
-                if (is_g) {
-                    uint32_t bit;
-                    if (lam == n) bit = s_n & 1u;                              // small layer: idx == lane == path (warp 0)
-                    else bit = (srow(lam, beta >> 5)[ps[(lam - 1) * 32 + path]] >> (beta & 31)) & 1u;
-                    y = x1 + (bit ? -x0 : x0);                                 // PolarCode.cpp:448-451
+                    x0 = src[0]; x1 = src[32];
                 } else {
-                    y = f_fast(x0, x1, tb);                                    // PolarCode.cpp:438-446
+                    x0 = (double)chan[0]; x1 = (double)chan[1];
                 }
-                if (lam == n) lam_n = y; else xrow(lam, beta)[path] = y;
+                lam_n = is_g ? x1 + ((s_n & 1u) ? -x0 : x0) : f_fast(x0, x1, tb);
+                return;
+            }
+            double* dst = xrow(lam, 0) + path;
+            if (lam == 1) {
+                // channel layer: reference pairs are (2k, 2k+1); the result lands at the bit-reversed position
+                for (int i = i0; i < M; i += di) {
+                    const double x0 = (double)chan[2 * i], x1 = (double)chan[2 * i + 1];
+                    const int beta = (int)(__brev((unsigned)i) >> (33 - n));
+                    double y;
+                    if (is_g) y = x1 + (((sw[(size_t)(beta >> 5) << 5] >> (beta & 31)) & 1u) ? -x0 : x0);
+                    else y = f_fast(x0, x1, tb);
+                    dst[(size_t)beta << 5] = y;
+                }
+                return;
+            }
+            const double* src = xrow(lam - 1, 0) + px[(lam - 2) * 32 + path];
+            if (is_g) {
+                for (int i = i0; i < M; i += di) {                             // PolarCode.cpp:448-451
+                    const double x0 = src[(size_t)i << 5], x1 = src[(size_t)(i + M) << 5];
+                    dst[(size_t)i << 5] = x1 + (((sw[(size_t)(i >> 5) << 5] >> (i & 31)) & 1u) ? -x0 : x0);
+                }
+            } else {
+                for (int i = i0; i < M; i += di)                               // PolarCode.cpp:438-446
+                    dst[(size_t)i << 5] = f_fast(src[(size_t)i << 5], src[(size_t)(i + M) << 5], tb);
             }
         };
 
