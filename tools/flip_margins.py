@@ -18,13 +18,16 @@ for (n, K, crc, L, eb, total) in settings:
     total = max(CH, int(total * scale) // CH * CH)
     pc = PolarCode(n, K, 0.32, crc)
     margin = torch.empty(CH, dtype=torch.float32, device="cuda")
-    flips, hist, nflip_err = [], np.zeros(8, np.int64), 0
+    flips, hist, nflip_err, strict_differ, strict_flagged = [], np.zeros(8, np.int64), 0, 0, 0
     taus = [1e-7, 3e-7, 1e-6, 3e-6, 1e-5, 3e-5, 1e-4, 3e-4]
     t0 = time.time()
     for first in range(0, total, CH):
         llr, truth = pc.synthesize(CH, [eb], seed=991, first_index=first)
         o32 = pc.decode_device(llr, L, mode="fp32", margin=margin)
         o64 = pc.decode_device(llr, L, mode="f64")
+        ost = pc.decode_device(llr, L, mode="strict")
+        strict_flagged += pc.last_flagged
+        strict_differ += int((ost != o64).any(dim=1).sum().item())
         diff = (o32 != o64).any(dim=1)
         m = margin.clone()
         for i, t in enumerate(taus):
@@ -33,7 +36,8 @@ for (n, K, crc, L, eb, total) in settings:
             flips += m[diff].cpu().tolist()
             nflip_err += int(((o32 != truth).any(dim=1) & (o64 != truth).any(dim=1) & diff).sum().item())
     row = dict(n=n, K=K, crc=crc, L=L, ebno=eb, codewords=total, differ=len(flips), margins_of_differing=sorted(flips),
-               differing_that_are_block_errors_in_both=nflip_err, flag_share={"%g" % t: hist[i] / total for i, t in enumerate(taus)},
+               differing_that_are_block_errors_in_both=nflip_err, strict_mode_differ=strict_differ,
+               strict_mode_second_pass_share=strict_flagged / total, flag_share={"%g" % t: hist[i] / total for i, t in enumerate(taus)},
                seconds=time.time() - t0)
     rows.append(row)
     print(json.dumps(row), flush=True)
