@@ -97,6 +97,10 @@ extern const FastVariant POLAR_CAT(kFastPart, POLAR_PART)[] = {
     // and changed nothing at list 4, profiles/r02_ab_round1_experiments.txt)
     POLAR_FAST_TM_SG(11, 3, 4, 0, 2, 8, 1),  // 49: list 1
     POLAR_FAST_TM_SG(11, 3, 4, 1, 2, 8, 1),  // 50: list 2
+    // N=8192: layers 3-5 in the scratch, layer 6 in tensor memory, layers 7-8 shared, 9-13 registers
+    POLAR_FAST_TM(13, 3, 7, 5, 16, 1), // 51: lists 17..32
+    POLAR_FAST_TM(13, 3, 7, 2, 4, 4),  // 52: lists 3..4
+    POLAR_FAST_TM(13, 3, 7, 0, 4, 4),  // 53: list 1
 #endif
 };
 extern const int POLAR_CAT(kFastPartN, POLAR_PART) = (int)(sizeof(POLAR_CAT(kFastPart, POLAR_PART)) / sizeof(FastVariant));

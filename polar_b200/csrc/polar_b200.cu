@@ -959,7 +959,7 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     memset(&a, 0, sizeof(a));
     int bps = env_int("POLAR_B200_EXACT_BPS", 3);
     if (bps < 1) bps = 1;
-    if (bps > 4) bps = 4;
+    if (bps > 8) bps = 8;
     const int budget = (220 * 1024) / bps;
     int off = 0;
     for (int lam = 0; lam <= n - 1; ++lam) { a.s_off[lam] = off; off += ((1 << (n - lam)) + 31) / 32; }

@@ -128,10 +128,10 @@ struct Cfg {
     static constexpr __host__ __device__ int ss_rows() { int r = 0; for (int j = 1; j <= SWL; ++j) if (!s_global(j)) r += swords(j); return r; }
     static constexpr int GS_ROWS = gs_rows();
     static constexpr int SS_ROWS = ss_rows();
-    // + 64 bytes of clone scatter / free-path stack, + 32 bytes for the decision-margin slots of the one-codeword-per-warp
+    // + 64 bytes of clone scatter / free-path stack, + 16 bytes for the decision-margin slot of the one-codeword-per-warp
     // kernels, which have no register to spare (the others keep the margin in a register; anything more per warp would
     // cost the N = 2048 variants their fourth block per SM)
-    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64 + (WLOG_ == 5 ? 32 : 0);
+    static constexpr int SMEM_PER_WARP = (SX_ROWS + SS_ROWS) * 128 + 64 + (WLOG_ == 5 ? 16 : 0);
     static constexpr int PA_FLOATS = MT + MT / 2;       // phase A: two walk buffers + one subtree buffer
     // lists <= 16 (G > 1 codewords per warp): the channel LLRs of the warp's codewords are staged TRANSPOSED
     // ([position / 4][codeword][4], so that a lane still reads float4) behind the XS arrays, which are stored
@@ -219,32 +219,15 @@ template <class P> __device__ __forceinline__ P* shfl_ptr(P* p, int src) {
 // unsaturated one. Two saturated keys compare equal, which shows up as a zero margin.
 constexpr float kQScale = 16777216.0f;
 constexpr uint32_t kQSat = 0xFFFFFFFFu;
-constexpr uint32_t kRelevanceSlack = 1u << 14;      // 2^-10 in Q8.24: far above the metrics' own error (a few 1e-6)
 __device__ __forceinline__ uint32_t q_of(float x) { return __float2uint_rn(x * kQScale); }        // x >= 0; saturates
 __device__ __forceinline__ uint32_t q_add(uint32_t a, uint32_t b) { const uint32_t r = a + b; return r < a ? kQSat : r; }
 
 // Decision margin: the gap (>= 0) between the worst fork that was kept and the best fork that was dropped. A gap
 // below the arithmetic's own error means the double-precision reference may decide otherwise; such codewords are
 // re-decoded in double (strict mode). Only gaps below tauq are recorded (the smallest one per codeword).
-//
-// Which close decisions can matter (one codeword per warp; slots in shared memory: mg[0] smallest gap, mg[2..3] the sum of
-// all renormalisation bases so far as a 64-bit integer, mg[4..5] the smallest ABSOLUTE metric (base sum + key) of a
-// worst-kept fork K at any close decision). If the reference swaps K for the best dropped fork D there, the two
-// decoders' lists differ from then on only in paths whose metric is >= metric(K): both keep, at every later prune, the
-// same candidates below that value (children of common paths, identical metrics), and whatever else fills the list lies
-// above it -- by induction over the leaves. Metrics never decrease. So if the final winner's absolute metric is below
-// every such metric(K) by more than the arithmetic's error, and it passed the parity check, the winner is a path both
-// decoders hold with the same metric and everything only one of them holds is worse: the close decisions could not have
-// changed the output and the codeword needs no second pass.
-template <int W> __device__ __forceinline__ void note_gap(const Warp& w, Lane& s, uint32_t gapq, uint32_t tauq, uint32_t keptq) {
-    if constexpr (W == 32) {
-        if (gapq < tauq && w.lane == 0) {            // rare: only sub-threshold gaps
-            atomicMin(w.mg, gapq);
-            unsigned long long* q = reinterpret_cast<unsigned long long*>(w.mg);
-            const unsigned long long thr = q[1] + keptq;
-            if (thr < q[2]) q[2] = thr;
-        }
-    } else s.mg = min(s.mg, gapq);                   // uniform over the lanes of a codeword
+template <int W> __device__ __forceinline__ void note_gap(const Warp& w, Lane& s, uint32_t gapq, uint32_t tauq) {
+    if constexpr (W == 32) { if (gapq < tauq && w.lane == 0) atomicMin(w.mg, gapq); }    // rare: only sub-threshold gaps
+    else s.mg = min(s.mg, gapq);                     // uniform over the lanes of a codeword
 }
 
 // ---- tensor memory as a per-warp scratch (tcgen05.ld/st, shape 32x32b: lane i of the warp <-> TMEM lane i of
@@ -965,7 +948,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 const unsigned ka = gmax<W>(s.active ? klo : 0u);
                 if (kb > ka) {
                     if (s.active) s.pm = klo;
-                    note_gap<W>(w, s, kb - ka, tauq, ka);
+                    note_gap<W>(w, s, kb - ka, tauq);
                     return like1 ? 1u : 0u;
                 }
             }
@@ -996,7 +979,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 keptA &= ~(1u << al);
                 kbl = kb; kal = ka;
             }
-            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq, max(kan, kbl));  // best dropped fork - worst kept fork
+            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);  // best dropped fork - worst kept fork
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1033,7 +1016,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             }
         }
         if (2 * A > L) {
-            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq, max(kan, kbl));
+            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);
             const bool ka_ = (keptA >> slot) & 1u, kb_ = (keptB >> slot) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1199,12 +1182,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         s.active = valid && (slot == c0);
         s.pm = 0u; s.px = 0; s.ps = 0; s.sreg = 0;
         w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
-        if constexpr (W == 32) {
-            if (lane == 0) {                            // no close decision so far; base sum 0
-                unsigned long long* q = reinterpret_cast<unsigned long long*>(w.mg);
-                w.mg[0] = kQSat; q[1] = 0ull; q[2] = ~0ull;
-            }
-        }
+        if constexpr (W == 32) { if (lane == 0) *w.mg = kQSat; }   // smallest decision margin so far: none recorded
         s.mg = (W == 1) ? 0x7F800000u : kQSat;
         __syncwarp();
         int sp = L - 1;
@@ -1238,9 +1216,6 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 // renormalise: metrics are kept relative to the best path of the list (exact integer subtraction)
                 const uint32_t base = gmin<W>(s.active ? s.pm : kQSat);
                 if (s.active && s.pm != kQSat) s.pm -= base;
-                if constexpr (W == 32) {
-                    if (lane == 0 && base != kQSat) reinterpret_cast<unsigned long long*>(w.mg)[1] += base;
-                }
             }
             const uint32_t frozen16 = (a.frozen_words[phi0 >> 5] >> (phi0 & 31)) & 0xFFFFu;
             if constexpr (POLAR_UNROLL2 && (W == 32 || W == 1)) {
@@ -1436,23 +1411,12 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             if constexpr (W == 32) mgq = *w.mg;
             else if constexpr (W == 1) mgq = q_of(__uint_as_float(s.mg));
             else mgq = s.mg;
-            uint32_t pickq = kQSat;                          // margin of the final pick alone
             if constexpr (W > 1) {
                 const unsigned second = gmin<W>((eligible && slot != win) ? s.pm : 0xFFFFFFFFu);
-                if (cand == 0) pickq = 0u;
-                else if (second != 0xFFFFFFFFu) pickq = second - best;
+                if (cand == 0) mgq = 0u;
+                else if (second != 0xFFFFFFFFu) mgq = min(mgq, second - best);
             }
-            bool close = mgq < a.tauq_flag;                  // some keep/drop decision was close
-            if constexpr (W == 32) {
-                if (close && cand != 0 && (a.crc == 0 || use_parity)) {
-                    // ... but none of them can have changed the output (see note_gap): the winner sits below every
-                    // worst-kept fork of a close decision by more than kRelevanceSlack
-                    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(w.mg);
-                    if (q[1] + best + kRelevanceSlack < q[2]) close = false;
-                }
-            }
-            mgq = min(mgq, pickq);
-            flagme = a.flag_list != nullptr && (close || pickq < a.tauq_flag);
+            flagme = a.flag_list != nullptr && mgq < a.tauq_flag;
             if (slot == 0 && valid) {
                 if (a.margin != nullptr) a.margin[a.cw_base + cw] = (mgq == kQSat) ? CUDART_INF_F : (float)mgq * (1.0f / kQScale);
                 if (flagme) a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;

@@ -65,6 +65,10 @@ PARITY = [
     (10, 512, 16, 32, 40, 1.5),      # N = 1024
     (8, 128, 8, 32, 80, 1.5),        # N = 256
     (12, 2048, 16, 8, 48, 1.5),
+    (13, 4096, 16, 32, 6, 2.0),      # N = 8192 (layers 3-5 in the scratch, layer 6 in tensor memory)
+    (13, 4096, 16, 4, 20, 2.0),
+    (13, 4096, 0, 1, 70, 2.5),
+    (13, 4096, 16, 8, 5, 2.0),       # N = 8192 without a fast variant for this list size: generic kernel
     (10, 512, 16, 1, 300, 2.0),      # other block lengths on the several-codewords-per-warp variants (lists 1..16)
     (10, 512, 16, 4, 200, 1.5),
     (10, 512, 0, 16, 70, 1.5),
@@ -101,7 +105,7 @@ def test_gpu_matches_oracle_on_awgn(torch_cuda, n, K, crc, L, B, eb):
     assert mism == 0, "%d of %d codewords differ from the oracle" % (mism, B)
 
 
-@pytest.mark.parametrize("n,K,crc,L,B,eb", [p for p in PARITY if p[0] >= 8 and p[0] <= 12])
+@pytest.mark.parametrize("n,K,crc,L,B,eb", [p for p in PARITY if 8 <= p[0] <= 12 or (p[0] == 13 and p[3] in (1, 4, 32))])
 def test_fp32_kernels_alone_match_oracle_on_awgn(torch_cuda, n, K, crc, L, B, eb):
     """mode="fp32": the throughput kernels without the double-precision second pass. Stated tolerance: at most one
     codeword of the batch (all of these batches are far smaller than the measured deviation rate would need)."""

@@ -31,4 +31,18 @@ for (n,K,crc,L,B) in [(9,256,16,8,4),(7,64,8,48,5),(8,100,7,127,2)]:
     same = np.array_equal(pc.decode_p1_batch(p1, p0, L), port.decode_p1_batch(p1, p0, L))
     ok &= same
     print(n, K, crc, L, B, "p1 kernel kind", pc.info(6), "ok" if same else "MISMATCH", flush=True)
+# strict mode with a huge threshold (most codewords take the second pass: block-per-codeword double kernel in list mode,
+# then the literal-formula kernel's list mode), the min-sum build, the fused-count sweep
+for (n,K,crc,L,B) in [(9,256,16,32,12),(11,1024,16,4,9),(9,256,0,1,40),(11,1024,16,32,4)]:
+    port = Port(n,K,0.32,crc); pc = PolarCode(n,K,0.32,crc)
+    info, llr = awgn_llrs(port, B, 1.0, 8)
+    want = port.decode_batch(llr, L)
+    pc.set_strict_tau(1e-3)
+    got = pc.decode_batch(llr, L, mode="strict")
+    nf = pc.last_flagged
+    ms = pc.decode_batch(llr, L, mode="minsum")
+    same = np.array_equal(got, want) and np.array_equal(ms, port.decode_batch(llr, L, minsum_only=2))
+    c = pc.bler_sweep_device([1.0, 2.0], [L], 64, seed=3, mode="strict")
+    ok &= same
+    print(n, K, crc, L, B, "strict: second pass on", nf, "of", B, "; sweep counts", c.tolist(), "ok" if same else "MISMATCH", flush=True)
 print("ALL OK" if ok else "FAIL")
