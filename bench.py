@@ -384,7 +384,10 @@ def run_ours(args):
         peak, peak_src = measured_peak()
         traffic, traffic_src = recorded_traffic(args.config, B)
         sm_count = code.info(1)
-        achieved = B * bytes_cw / (ms_step * 1e-3) / 1e9     # per GPU: one launch decodes this rank's B codewords
+        # the dominant kernel (scl_fast_kernel) alone: in strict / f64 mode the step also holds the second pass, so its
+        # launch duration is the fp32 arm's step (the same kernel, one launch per step, timed with CUDA events above)
+        kernel_ms = ms_other if mode in ("strict", "f64") else ms_step
+        achieved = B * bytes_cw / (kernel_ms * 1e-3) / 1e9   # per GPU: one launch decodes this rank's B codewords
         strict_flagged = flagged if mode == "strict" else flagged_other
         out = {
             "metric": "codewords/sec", "value": value, "unit": "codewords/s", "n_gpus": world, "steps": args.steps,
@@ -408,7 +411,7 @@ def run_ours(args):
                          "traffic_note": "dram bytes/codeword of the committed ncu --set full capture (batch %s) x this batch"
                                          % (traffic_src or {}).get("captured_batch", "16384"),
                          "kernel": "scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel",
-                         "kernel_kind": code.info(6), "kernel_ms": ms_step},
+                         "kernel_kind": code.info(6), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step},
             "modes": {mode: value, other: world * B / (ms_other * 1e-3), "unit": "codewords/s (device-resident)",
                       "strict_flagged_per_step": strict_flagged, "strict_flag_rate": strict_flagged / float(world * B),
                       "codewords_differing_between_modes": differs_between_modes},
