@@ -318,6 +318,8 @@ __device__ __forceinline__ float f_rule(float a, float b) { return sign_min(a, b
 __device__ __forceinline__ float softplus_ref(float x) { return fmaxf(x, 0.0f); }
 __device__ __forceinline__ float log1p_exp_neg(float) { return 0.0f; }
 #endif
+// log(1 + e^x) for the fixed-point metric: the reference's corner cases (softplus_ref) fall out of q_of by themselves
+__device__ __forceinline__ float softplus_q(float x) { return fmaxf(x, 0.0f) + log1p_exp_neg(fabsf(x)); }
 __device__ __forceinline__ void f_rule2(float a0, float b0, float a1, float b1, float& y0, float& y1) {
 #if POLAR_MINSUM
     y0 = sign_min(a0, b0); y1 = sign_min(a1, b1);
@@ -931,8 +933,11 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
 #if POLAR_MINSUM
     const uint32_t klo = s.pm, khi = q_add(s.pm, q_of(ax));                       // hardware-friendly metric
 #else
-    const uint32_t klo = q_add(s.pm, q_of((ax >= 36.7368f) ? 0.0f : t));                       // likely fork
-    const uint32_t khi = q_add(s.pm, q_of((ax >= 709.78271484375f) ? CUDART_INF_F : ax + t));  // unlikely fork
+    // The double reference's corner cases need no code here: its log(1 + e^-|x|) rounds to exactly 0 from |x| = 36.74 on
+    // (1e-16, far below the fixed point's 6e-8 step: q_of gives 0 too), and its +inf from |x| = 709.78 on (exp overflow)
+    // lies beyond the saturation at 256, like every other hopeless fork.
+    const uint32_t klo = q_add(s.pm, q_of(t));                                    // likely fork
+    const uint32_t khi = q_add(s.pm, q_of(ax + t));                               // unlikely fork
 #endif
     const uint32_t m0 = neg ? khi : klo, m1 = neg ? klo : khi;
     const unsigned act = gballot<W>(s.active, gbase);
@@ -1240,7 +1245,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 }
                 uint32_t u = 0;
                 if ((frozen16 >> j) & 1u) {
-                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_ref(-lam_n))); }   // PolarCode.cpp:475-487
+                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_q(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
                     u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
@@ -1293,7 +1298,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                 }
                 uint32_t u = 0;
                 if ((frozen16 >> j) & 1u) {
-                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_ref(-lam_n))); }   // PolarCode.cpp:475-487
+                    if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_q(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
                     u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
