@@ -24,10 +24,29 @@ def _need(path):
     return path
 
 
+def _preload_nccl():
+    """polar_b200_comm_* dlopens "libnccl.so.2" at first use. In a process that also runs torch the copy torch was
+    built against (the nvidia-nccl wheel next to it) must be the one in the process: if the system's older libnccl got
+    loaded first, torch's own import would later bind to it and fail on missing symbols. So the wheel's library, when
+    there is one, is loaded here before anything else can ask for that SONAME."""
+    try:
+        import glob
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            for p in sorted(glob.glob(os.path.join(d, "lib", "libnccl.so*"))):
+                C.CDLL(p, mode=C.RTLD_GLOBAL)
+                return p
+    except Exception:
+        pass
+    return None
+
+
 def dev():
     """libpolar_b200.so with argtypes set for every symbol of include/polar_b200.h."""
     global _dev
     if _dev is None:
+        _preload_nccl()
         lib = C.CDLL(_need(DEV_SO), mode=C.RTLD_GLOBAL)
         vp, ip = C.c_void_p, C.c_int
         lib.polar_b200_abi_version.restype = ip

@@ -1653,7 +1653,10 @@ struct NcclApi {
 const NcclApi& nccl_api() {
     static NcclApi api = [] {
         NcclApi a;
-        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        // the copy already in the process (a host framework's) wins; POLAR_B200_NCCL_LIB names another one explicitly
+        const char* forced = getenv("POLAR_B200_NCCL_LIB");
+        if (forced && *forced) a.lib = dlopen(forced, RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
         if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (!a.lib) return a;
         a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(a.lib, "ncclGetUniqueId");
