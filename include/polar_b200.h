@@ -261,9 +261,17 @@ enum {
                                             1000 + i = min-sum build i, -2 = wide-list kernel (lists 33..127),
                                             -3 = wide-list kernel in f64, -4 = probability-domain decoder */
     POLAR_B200_INFO_HOST_CHUNKS = 7,     /* chunks the last *_host call was pipelined in            */
-    POLAR_B200_INFO_LAST_FLAGGED = 8     /* codewords the last STRICT call decoded again in double (waits for it) */
+    POLAR_B200_INFO_LAST_FLAGGED = 8,    /* codewords the last STRICT call decoded again in double (waits for it) */
+    POLAR_B200_INFO_LAST_RECORDED = 9    /* close decisions the last STRICT call checked in double instead (lists 17..32) */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
+
+/*
+ * Test hook: the close decisions the last STRICT call recorded (lists 17..32), as the first pass saw them (fp32 gap
+ * between the best dropped and the worst kept fork) and as the verify kernel recomputed them in double, plus the codeword
+ * each belongs to. Host arrays of `cap` entries (any may be NULL); returns the number of records copied.
+ */
+int polar_b200_debug_verify_gaps(polar_b200_ctx* ctx, float* gap_fp32, double* gap_f64, int* codeword, int cap);
 
 #ifdef __cplusplus
 }
