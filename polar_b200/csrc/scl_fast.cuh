@@ -1055,7 +1055,8 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 if (kb > ka) {
                     if (kb - ka < tauq) {                  // rare: a close decision
                         note_gap<W>(w, s, kb - ka, tauq);
-                        close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, act, 0u, act, __ballot_sync(FULL_MASK, like1),
+                        if (vrec != nullptr)
+                            close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, act, 0u, act, __ballot_sync(FULL_MASK, like1),
                                           s.ps, s.sreg, phi, cw, tauq, vrec, vcount, vcap);
                     }
                     if (s.active) s.pm = klo;
@@ -1091,7 +1092,8 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
             }
             if (min(kbn, kal) - max(kan, kbl) < tauq) {    // rare: best dropped fork - worst kept fork is small
                 note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);
-                close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, keptA, keptB, act, lk, s.ps, s.sreg, phi, cw, tauq,
+                if (vrec != nullptr)
+                    close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, keptA, keptB, act, lk, s.ps, s.sreg, phi, cw, tauq,
                                   vrec, vcount, vcap);
             }
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
