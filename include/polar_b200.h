@@ -266,13 +266,6 @@ enum {
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
 
-/*
- * Test hook: the close decisions the last STRICT call recorded (lists 17..32), as the first pass saw them (fp32 gap
- * between the best dropped and the worst kept fork) and as the verify kernel recomputed them in double, plus the codeword
- * each belongs to. Host arrays of `cap` entries (any may be NULL); returns the number of records copied.
- */
-int polar_b200_debug_verify_gaps(polar_b200_ctx* ctx, float* gap_fp32, double* gap_f64, int* codeword, int cap);
-
 #ifdef __cplusplus
 }
 #endif

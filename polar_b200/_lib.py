@@ -79,7 +79,6 @@ def dev():
         lib.polar_b200_comm_allreduce_i64.argtypes = [vp, vp, ip]
         lib.polar_b200_comm_allreduce_i64_group.argtypes = [vp, ip, vp, ip]
         lib.polar_b200_comm_destroy.argtypes = [vp]
-        lib.polar_b200_debug_verify_gaps.argtypes = [vp, vp, vp, vp, ip]
         lib.polar_b200_get_info.restype = C.c_longlong
         lib.polar_b200_get_info.argtypes = [vp, ip]
         _dev = lib

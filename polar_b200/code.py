@@ -214,17 +214,6 @@ class PolarCode:
         """codewords the last strict-mode call decoded again in double (synchronises)"""
         return self.info(8)
 
-    @property
-    def last_recorded(self):
-        """close decisions the last strict-mode call checked in double instead of re-decoding the codeword (synchronises)"""
-        return self.info(9)
-
-    def verify_gaps(self, cap=1 << 20):
-        """test hook (polar_b200_debug_verify_gaps): (fp32 gap, double gap, codeword) of every recorded close decision"""
-        g32, g64, cw = np.zeros(cap, np.float32), np.zeros(cap, np.float64), np.zeros(cap, np.int32)
-        n = _lib.dev().polar_b200_debug_verify_gaps(self.ctx(1), g32.ctypes.data, g64.ctypes.data, cw.ctypes.data, cap)
-        return g32[:n], g64[:n], cw[:n]
-
     def set_strict_tau(self, tau):
         _lib.check(_lib.dev().polar_b200_set_strict_tau(self.ctx(1), float(tau)))
 

@@ -60,7 +60,6 @@ typedef enum { ncclSum = 0 } ncclRedOp_t;
 #include "fast_variants.cuh"
 #include "scl_wide.cuh"
 #include "scl_exact.cuh"
-#include "scl_verify.cuh"
 
 namespace {
 
@@ -550,12 +549,6 @@ struct polar_b200_ctx {
     uint32_t* d_sw_out = nullptr;
     unsigned long long* d_sw_err = nullptr;
     int sw_chunk = 0, sw_cells = 0;
-    uint32_t* d_vrec = nullptr;            // strict mode, lists 17..32: recorded close decisions (scl_verify.cuh)
-    int* d_vcount = nullptr;               // [1]
-    int* d_cw_state = nullptr;             // [state_cap]: 1 once a codeword is on the flag list
-    double* d_vgap = nullptr;              // [vcap] double-precision gap per record (debug / tests)
-    int vcap = 0, vrec_words = 0, state_cap = 0;
-    long long last_verified = -1;
     double* d_ex_gx = nullptr;             // scratch of the block-per-codeword double decoder (scl_exact.cuh), grow-only
     size_t ex_gx_bytes = 0;
     double* d_cvt = nullptr;               // float -> double conversion buffer of the kernels that take one input type
@@ -836,7 +829,7 @@ int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_
 // variant >= 0: entry of the reference-arithmetic table; variant <= -100: entry -100 - variant of the min-sum table.
 int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, uint32_t* out, cudaStream_t st,
                 float* margin = nullptr, int* flag_list = nullptr, int* flag_count = nullptr, float tau = 0.0f, int cw_base = 0,
-                const CountSpec* cs = nullptr, bool record_close = false) {
+                const CountSpec* cs = nullptr) {
     const FastVariant& v = variant <= -100 ? kFastMsPart[-100 - variant] : kFastVariants[variant];
     int blocks = c->sm_count * v.bps;
     const int warps = blocks * v.wpb;
@@ -882,8 +875,6 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
     a.margin = margin; a.flag_list = flag_list; a.flag_count = flag_count; a.cw_base = cw_base;
     a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
     a.first_index = cs ? cs->first_index : 0; a.n_ebno = cs ? cs->n_ebno : 1;
-    a.vrec = record_close ? c->d_vrec : nullptr; a.vcount = c->d_vcount; a.vcap = c->vcap;
-    a.cw_state = record_close ? c->d_cw_state : nullptr;
     {
         // thresholds in the kernels' fixed point (Q8.24). With a margin buffer every gap is recorded (calibration);
         // otherwise only those that will flag the codeword.
@@ -1091,58 +1082,13 @@ float strict_tau(const polar_b200_ctx* c) {
     return c->strict_tau;
 }
 
-// buffers of the close-decision records (lists 17..32): room for one record per 8 codewords (about ten times what
-// tau = 1e-5 produces; the first pass flags a codeword itself when there is no room)
-int ensure_verify(polar_b200_ctx* c, int B) {
-    const int words = 4 + 2 * c->NW;
-    int cap = B / 8;
-    if (cap < 1024) cap = 1024;
-    if (!c->d_vcount) CU_TRY(cudaMalloc(&c->d_vcount, sizeof(int)));
-    if (cap > c->vcap || words != c->vrec_words) {
-        if (c->d_vrec) cudaFree(c->d_vrec);
-        if (c->d_vgap) cudaFree(c->d_vgap);
-        c->d_vrec = nullptr; c->d_vgap = nullptr; c->vcap = 0;
-        CU_TRY(cudaMalloc(&c->d_vrec, (size_t)cap * words * sizeof(uint32_t)));
-        CU_TRY(cudaMalloc(&c->d_vgap, (size_t)cap * sizeof(double)));
-        c->vcap = cap; c->vrec_words = words;
-    }
-    if (B > c->state_cap) {
-        if (c->d_cw_state) cudaFree(c->d_cw_state);
-        c->d_cw_state = nullptr; c->state_cap = 0;
-        CU_TRY(cudaMalloc(&c->d_cw_state, (size_t)B * sizeof(int)));
-        c->state_cap = B;
-    }
-    return 0;
-}
-bool verify_applies(const polar_b200_ctx* c, int L) {
-    return L > 16 && L <= 32 && c->n >= 8 && c->n <= 13 && env_int("POLAR_B200_VERIFY", 1) != 0;
-}
-int launch_verify(polar_b200_ctx* c, const float* llr, cudaStream_t st) {
-    verify::Args a;
-    a.llr = llr; a.vrec = c->d_vrec; a.vcount = c->d_vcount; a.vcap = c->vcap; a.frozen_words = c->d_frozen;
-    a.flag_list = c->d_flag_list; a.flag_count = c->d_flag_count; a.cw_state = c->d_cw_state; a.n = c->n;
-    a.gap_out = c->d_vgap;
-    const int smem = 2 * c->N * (int)sizeof(double) + (c->n + 1) * c->NW * 4 + (verify::NT / 32 + 2) * 8 + (int)sizeof(exact::Tables) + 16;
-    CU_TRY(cudaFuncSetAttribute(verify::verify_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    int per_sm = (200 * 1024) / smem;
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
-    verify::verify_kernel<<<c->sm_count * per_sm, verify::NT, smem, st>>>(a);
-    CU_TRY(cudaGetLastError());
-    c->launches += 1;
-    return 0;
-}
-
 // Device-resident decode in one of the three arithmetic modes (include/polar_b200.h). llr / out: device pointers.
 // cw_base / zero_count / redecode serve the chunked host entry point: chunks share one flag list and are re-decoded
 // together after the last chunk.
 // cs: count block errors against cs->truth (fused into the kernels' tails where they support it, a separate small kernel
 // otherwise; `out` must then be a real buffer).
-// record_only_chunk: a chunk of the host pipeline that records close decisions for the verify kernel the pipeline runs after
-// its last chunk.
 int decode_mode(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out, int mode, float* margin, cudaStream_t st,
-                int fv_forced = -2, int cw_base = 0, bool zero_count = true, bool redecode = true, const CountSpec* cs = nullptr,
-                bool record_only_chunk = false) {
+                int fv_forced = -2, int cw_base = 0, bool zero_count = true, bool redecode = true, const CountSpec* cs = nullptr) {
     auto count_after = [&](int rc) {
         if (rc || !cs) return rc;
         count_errors_bucket_kernel<<<(B + 255) / 256, 256, 0, st>>>(out, cs->truth, B, c->KW, cs->first_index, cs->n_ebno, cs->err);
@@ -1168,25 +1114,14 @@ int decode_mode(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out
         return count_after(decode_any<float>(c, llr, B, L, out, st));
     }
     if (mode == POLAR_B200_MODE_F64 || fv < 0) return count_after(decode_f64_from_float(c, llr, B, L, out, st));
-    // strict: fp32 everywhere, double where a decision was closer than tau. Lists 17..32: a close decision between
-    // exactly two forks is recorded and checked in double by the verify kernel; only what fails there, and what could
-    // not be recorded, is decoded again. (Not with fused counting, and not when the caller wants the flags back.)
+    // strict: fp32 everywhere, double where a decision was closer than tau
     int rc = ensure_flags(c, cw_base + B);
     if (rc) return rc;
-    const bool record = verify_applies(c, L) && !cs && (redecode || record_only_chunk);
-    if (record && (rc = ensure_verify(c, cw_base + B))) return rc;
-    if (zero_count) {
-        CU_TRY(cudaMemsetAsync(c->d_flag_count, 0, sizeof(int), st));
-        if (record) {
-            CU_TRY(cudaMemsetAsync(c->d_vcount, 0, sizeof(int), st));
-            CU_TRY(cudaMemsetAsync(c->d_cw_state, 0, (size_t)c->state_cap * sizeof(int), st));
-        }
-    }
-    rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, strict_tau(c), cw_base, cs, record);
+    if (zero_count) CU_TRY(cudaMemsetAsync(c->d_flag_count, 0, sizeof(int), st));
+    rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, strict_tau(c), cw_base, cs);
     if (rc) return rc;
     c->flagged_pending = true;
     if (!redecode) return POLAR_B200_OK;
-    if (record && (rc = launch_verify(c, llr, st))) return rc;
     return redecode_flagged(c, llr, B, L, out, st, cs);
 }
 
@@ -1287,7 +1222,6 @@ int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32
     c->last_chunks = nchunks;
     const bool final_copy = strict && redecode_on_device;     // the re-decode rewrites rows of earlier chunks
     if (strict && (rc = ensure_flags(c, B))) return rc;       // one flag list for all chunks: sized before the first launch
-    if (final_copy && verify_applies(c, L) && (rc = ensure_verify(c, B))) return rc;
     for (int i = 0; i < nchunks; ++i) {
         const long long lo = bounds[i];
         const int nb = (int)(bounds[i + 1] - lo);
@@ -1297,7 +1231,7 @@ int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32
                                cudaMemcpyHostToDevice, c->st_h2d));
         CU_TRY(cudaEventRecord(c->ev_in[i], c->st_h2d));
         CU_TRY(cudaStreamWaitEvent(c->st_run, c->ev_in[i], 0));
-        rc = decode_mode(c, d_in, nb, L, d_o, mode, nullptr, c->st_run, fv, (int)lo, i == 0, false, nullptr, final_copy);
+        rc = decode_mode(c, d_in, nb, L, d_o, mode, nullptr, c->st_run, fv, (int)lo, i == 0, false);
         if (rc) return rc;
         if (final_copy) continue;
         CU_TRY(cudaEventRecord(c->ev_done[i], c->st_run));
@@ -1306,7 +1240,6 @@ int host_pipeline(polar_b200_ctx* c, const float* llr_host, int B, int L, uint32
                                cudaMemcpyDeviceToHost, c->st_d2h));
     }
     if (final_copy) {
-        if (verify_applies(c, L) && (rc = launch_verify(c, c->d_llr_stage, c->st_run))) return rc;
         rc = redecode_flagged(c, c->d_llr_stage, B, L, c->d_out_stage, c->st_run);
         if (rc) return rc;
         CU_TRY(cudaMemcpyAsync(info_packed_host, c->d_out_stage, (size_t)B * c->KW * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->st_run));
@@ -1438,7 +1371,6 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
     cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt); cudaFree(c->d_ex_gx);
     cudaFree(c->d_sw_llr); cudaFree(c->d_sw_truth); cudaFree(c->d_sw_out); cudaFree(c->d_sw_err);
-    cudaFree(c->d_vrec); cudaFree(c->d_vcount); cudaFree(c->d_cw_state); cudaFree(c->d_vgap);
     cudaFreeHost(c->h_f32); cudaFreeHost(c->h_list); cudaFreeHost(c->h_gather); cudaFreeHost(c->h_out2);
     if (c->ev_last) cudaEventDestroy(c->ev_last);
     if (c->st_h2d) {
@@ -1837,26 +1769,6 @@ int polar_b200_comm_destroy(polar_b200_comm* m) {
     return POLAR_B200_OK;
 }
 
-int polar_b200_debug_verify_gaps(polar_b200_ctx* c, float* gap_fp32, double* gap_f64, int* codeword, int cap) {
-    if (!c || !c->d_vcount || !c->d_vrec) return 0;
-    cudaSetDevice(c->device);
-    drain(c);
-    int nv = 0;
-    if (cudaMemcpy(&nv, c->d_vcount, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    if (nv > c->vcap) nv = c->vcap;
-    if (nv > cap) nv = cap;
-    std::vector<uint32_t> rec((size_t)nv * c->vrec_words);
-    std::vector<double> g((size_t)nv);
-    if (nv && cudaMemcpy(rec.data(), c->d_vrec, rec.size() * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    if (nv && cudaMemcpy(g.data(), c->d_vgap, g.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-    for (int i = 0; i < nv; ++i) {
-        if (gap_fp32) gap_fp32[i] = (float)rec[(size_t)i * c->vrec_words + 3] * (1.0f / 16777216.0f);
-        if (gap_f64) gap_f64[i] = g[i];
-        if (codeword) codeword[i] = (int)rec[(size_t)i * c->vrec_words];
-    }
-    return nv;
-}
-
 long long polar_b200_get_info(polar_b200_ctx* c, int key) {
     if (!c) return -1;
     switch (key) {
@@ -1868,14 +1780,6 @@ long long polar_b200_get_info(polar_b200_ctx* c, int key) {
         case POLAR_B200_INFO_SCRATCH_BYTES: return (long long)c->scratch_bytes;
         case POLAR_B200_INFO_KERNEL_KIND: return c->last_kernel;
         case POLAR_B200_INFO_HOST_CHUNKS: return c->last_chunks;
-        case POLAR_B200_INFO_LAST_RECORDED: {
-            if (!c->d_vcount) return 0;
-            int nv = 0;
-            cudaSetDevice(c->device);
-            drain(c);
-            if (cudaMemcpy(&nv, c->d_vcount, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
-            return nv;
-        }
         case POLAR_B200_INFO_LAST_FLAGGED:
             if (c->flagged_pending) {
                 int nf = 0;

@@ -64,15 +64,6 @@ struct Args {
     float tau;         // plain SC: |LLR| below tau is recorded;  lists: gaps below tauq (Q8.24)
     uint32_t tauq;
     uint32_t tauq_flag;// codewords whose smallest recorded margin is below this are appended to flag_list
-    // list 32: a close keep/drop decision with exactly one kept and one dropped fork near the cut is not flagged but
-    // RECORDED (vrec, may be null: then every close decision flags): [0] codeword, [1] leaf, [2] kept lane | kept bit << 8
-    // | dropped lane << 16 | dropped bit << 24, [3] the gap (Q8.24), then the two parent paths' partial sums below the leaf, N bits
-    // each. polar_b200.cu's verify kernel recomputes the two fork metrics in double and flags the codeword only if the
-    // reference would have decided the other way.
-    uint32_t* vrec;
-    int* vcount;
-    int vcap;
-    int* cw_state;     // with vrec: [B], set to 1 for every codeword put on the flag list (the verify kernel appends too)
     int cw_base;       // index of llr's row 0 in the caller's batch (margin / flag_list are indexed by batch position)
     // block-error counting fused into the tail (the comparison loop of the BLER harness, PolarCode.cpp:758-769):
     // truth (may be null): [B][KW] packed info bits; err: one counter per Eb/N0 point, codeword with global index g
@@ -918,104 +909,12 @@ __device__ __forceinline__ void descend_block(const Warp& w, Lane& s, Sub& r, in
     else layer_to_regs<C, false>(w, s, r);
 }
 
-// 64-bit warp reductions for the rare path below
-__device__ __forceinline__ unsigned long long wmax64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL_MASK, v, o); v = t > v ? t : v; }
-    return v;
-}
-__device__ __forceinline__ unsigned long long wmin64(unsigned long long v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL_MASK, v, o); v = t < v ? t : v; }
-    return v;
-}
-
-__device__ __forceinline__ unsigned long long pick_max(unsigned long long a, unsigned long long b) { return a > b ? a : b; }
-__device__ __forceinline__ unsigned long long pick_min(unsigned long long a, unsigned long long b) { return a < b ? a : b; }
-
-// ---- a close decision at leaf phi (one codeword per warp; rare, out of line) ----
-// keptA / keptB: lanes whose likely / unlikely fork was kept; act: active lanes; lk: lanes whose likely fork is bit 1.
-// If the worst kept fork K and the best dropped fork D are the only forks within tauq of the cut, the decision is
-// recorded for the verify kernel: both parents' decided bits below phi, i.e. the partial sums of the completed left
-// siblings along the path to phi (layer lam holds them exactly when bit NLOG - lam of phi is set), each block at the
-// bit position of its first leaf. Otherwise (or when there is no room) the codeword is marked for the full second pass.
-template <class C>
-__device__ __noinline__ void close_decision(uint32_t* gs, uint32_t* ss, uint32_t* mg, int lane, uint32_t klo, uint32_t khi,
-                                            unsigned keptA, unsigned keptB, unsigned act, unsigned lk, unsigned long long ps,
-                                            uint32_t sreg, int phi, int cw, uint32_t tauq, uint32_t* vrec, int* vcount, int vcap) {
-    constexpr int NLOG = C::NLOG, NW = C::NW;
-    Warp w;
-    w.gs = gs; w.ss = ss; w.lane = lane;
-    const bool kA = (keptA >> lane) & 1u, kB = (keptB >> lane) & 1u, on = (act >> lane) & 1u;
-    const unsigned likely_bit = (lk >> lane) & 1u;
-    // forks ordered by (metric, fork index), fork index = 2 * lane + bit
-    const unsigned long long clo = ((unsigned long long)klo << 8) | (2u * lane + likely_bit);
-    const unsigned long long chi = ((unsigned long long)khi << 8) | (2u * lane + (likely_bit ^ 1u));
-    const unsigned long long none_hi = ~0ull;
-    const unsigned long long k1 = wmax64(kA ? (kB ? (clo > chi ? clo : chi) : clo) : (kB ? chi : 0ull));          // worst kept
-    const unsigned long long d1 = wmin64((on && !kA) ? ((on && !kB) ? (clo < chi ? clo : chi) : clo) : ((on && !kB) ? chi : none_hi));
-    const unsigned long long k2 = wmax64(pick_max(kA && clo != k1 ? clo : 0ull, kB && chi != k1 ? chi : 0ull));
-    const unsigned long long d2 = wmin64(pick_min((on && !kA && clo != d1) ? clo : none_hi, (on && !kB && chi != d1) ? chi : none_hi));
-    const uint32_t kk1 = (uint32_t)(k1 >> 8), kd1 = (uint32_t)(d1 >> 8);
-    bool simple = (k1 != 0ull) && (d1 != none_hi) && kk1 != kQSat && kd1 != kQSat;
-    if (k2 != 0ull && kd1 - (uint32_t)(k2 >> 8) < tauq) simple = false;           // a second kept fork is close to the cut
-    if (d2 != none_hi && (uint32_t)(d2 >> 8) - kk1 < tauq) simple = false;        // a second dropped fork is close to the cut
-    const uint32_t state = mg[1];
-    if ((state >> 8) >= 4u) simple = false;                                       // at most four records per codeword
-    int slot = -1;
-    if (simple) {
-        if (lane == 0) slot = atomicAdd(vcount, 1);
-        slot = __shfl_sync(FULL_MASK, slot, 0);
-        if (slot >= vcap) simple = false;
-    }
-    if (!simple) {
-        if (lane == 0) mg[1] = state | 1u;
-        __syncwarp();
-        return;
-    }
-    if (lane == 0) mg[1] = state + 256u;
-    uint32_t* rec = vrec + (size_t)slot * (4 + 2 * NW);
-    const int lK = (int)((k1 & 0xFFu) >> 1), lD = (int)((d1 & 0xFFu) >> 1);
-    if (lane == 0) {
-        rec[0] = (uint32_t)cw; rec[1] = (uint32_t)phi;
-        rec[2] = (uint32_t)lK | ((uint32_t)(k1 & 1u) << 8) | ((uint32_t)lD << 16) | ((uint32_t)(d1 & 1u) << 24);
-        rec[3] = kd1 - kk1;                          // the gap as the first pass saw it (Q8.24), for cross-checks
-    }
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {
-        const int l = which ? lD : lK;
-        const unsigned long long psl = __shfl_sync(FULL_MASK, ps, l);
-        const uint32_t sregl = __shfl_sync(FULL_MASK, sreg, l);
-        uint32_t* dst = rec + 4 + which * NW;
-#pragma unroll 1
-        for (int lam = 1; lam <= C::SWL; ++lam) {
-            if (!((phi >> (NLOG - lam)) & 1)) continue;
-            const int mw = (C::N >> lam) / 32;
-            const int off = ((phi >> (NLOG - lam + 1)) << (NLOG - lam + 1)) >> 5;
-            const uint32_t* src = sbase_rt<C>(w, lam) + get_ptr(psl, lam - 1);
-            for (int x = lane; x < mw; x += 32) dst[off + x] = src[x * 32];
-        }
-        if (lane == 0) {
-            uint32_t wl = 0;                         // the five deepest layers: fields of the packed register
-#pragma unroll
-            for (int k = 0; k < 5; ++k)
-                if ((phi >> k) & 1) {
-                    const uint32_t field = (sregl >> ((1 << k) - 1)) & ((1u << (1 << k)) - 1u);
-                    wl |= field << (((phi >> (k + 1)) << (k + 1)) & 31);
-                }
-            dst[phi >> 5] = wl;
-        }
-    }
-    __syncwarp();
-}
-
 // ---- fork / prune at an unfrozen bit (PolarCode.cpp:489-607); W lanes = the list of one codeword ----
 // Returns the decided bit of this lane's (possibly new) path. `permuted` is warp-uniform.
 // tauq / tau: decision gaps below this (fixed point / float for plain SC) are recorded in the warp's margin slots.
 template <class C>
 __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_n, int L, int& sp, bool& permuted,
-                                              int& src_lane, uint32_t tauq, float tau, int phi, int cw, uint32_t* vrec,
-                                              int* vcount, int vcap) {
+                                              int& src_lane, uint32_t tauq, float tau) {
     constexpr int W = C::W;
     const int lane = w.lane;
     const int gbase = lane & ~(W - 1), slot = lane & (W - 1);
@@ -1053,13 +952,8 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 const unsigned kb = gmin<W>(s.active ? khi : 0xFFFFFFFFu);
                 const unsigned ka = gmax<W>(s.active ? klo : 0u);
                 if (kb > ka) {
-                    if (kb - ka < tauq) {                  // rare: a close decision
-                        note_gap<W>(w, s, kb - ka, tauq);
-                        if (vrec != nullptr)
-                            close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, act, 0u, act, __ballot_sync(FULL_MASK, like1),
-                                          s.ps, s.sreg, phi, cw, tauq, vrec, vcount, vcap);
-                    }
                     if (s.active) s.pm = klo;
+                    note_gap<W>(w, s, kb - ka, tauq);
                     return like1 ? 1u : 0u;
                 }
             }
@@ -1090,12 +984,7 @@ __device__ __forceinline__ uint32_t info_step(const Warp& w, Lane& s, float lam_
                 keptA &= ~(1u << al);
                 kbl = kb; kal = ka;
             }
-            if (min(kbn, kal) - max(kan, kbl) < tauq) {    // rare: best dropped fork - worst kept fork is small
-                note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);
-                if (vrec != nullptr)
-                    close_decision<C>(w.gs, w.ss, w.mg, lane, klo, khi, keptA, keptB, act, lk, s.ps, s.sreg, phi, cw, tauq,
-                                  vrec, vcount, vcap);
-            }
+            note_gap<W>(w, s, min(kbn, kal) - max(kan, kbl), tauq);  // best dropped fork - worst kept fork
             const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
             keep0 = like1 ? kb_ : ka_;
             keep1 = like1 ? ka_ : kb_;
@@ -1298,7 +1187,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
         s.active = valid && (slot == c0);
         s.pm = 0u; s.px = 0; s.ps = 0; s.sreg = 0;
         w.stack[lane] = (unsigned char)slot;            // free stack 0..L-2 of every codeword (entries >= sp are don't-care)
-        if constexpr (W == 32) { if (lane == 0) { w.mg[0] = kQSat; w.mg[1] = 0u; } }   // no close decision so far
+        if constexpr (W == 32) { if (lane == 0) *w.mg = kQSat; }   // smallest decision margin so far: none recorded
         s.mg = (W == 1) ? 0x7F800000u : kQSat;
         __syncwarp();
         int sp = L - 1;
@@ -1359,7 +1248,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                     if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_q(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
-                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau, phi0 + j, a.cw_base + cw, a.vrec, a.vcount, a.vcap);
+                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
                     if (permuted) {
                         // a cloned path takes over its parent's subtree registers -- those that are still live:
                         // x4 is read again at leaf 8, x3 at leaves 4 and 12, x2 at leaves 2 mod 4, x1 at odd leaves
@@ -1412,7 +1301,7 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
                     if constexpr (W != 1) { if (s.active) s.pm = q_add(s.pm, q_of(softplus_q(-lam_n))); }   // PolarCode.cpp:475-487
                 } else {
                     bool permuted; int src_lane;
-                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau, phi0 + j, a.cw_base + cw, a.vrec, a.vcount, a.vcap);
+                    u = info_step<C>(w, s, lam_n, L, sp, permuted, src_lane, a.tauq, a.tau);
                     if (permuted) {
                         // a cloned path takes over its parent's live subtree registers
 #pragma unroll
@@ -1527,27 +1416,15 @@ __global__ void __launch_bounds__(WPB * 32, BPS) scl_fast_kernel(const Args a) {
             if constexpr (W == 32) mgq = *w.mg;
             else if constexpr (W == 1) mgq = q_of(__uint_as_float(s.mg));
             else mgq = s.mg;
-            bool pick_close = false;
             if constexpr (W > 1) {
                 const unsigned second = gmin<W>((eligible && slot != win) ? s.pm : 0xFFFFFFFFu);
-                uint32_t pq = kQSat;
-                if (cand == 0) pq = 0u;
-                else if (second != 0xFFFFFFFFu) pq = second - best;
-                pick_close = pq < a.tauq_flag;
-                mgq = min(mgq, pq);
+                if (cand == 0) mgq = 0u;
+                else if (second != 0xFFFFFFFFu) mgq = min(mgq, second - best);
             }
             flagme = a.flag_list != nullptr && mgq < a.tauq_flag;
-            if constexpr (W == 32) {
-                // close keep/drop decisions that were recorded for the verify kernel do not flag the codeword here: only a
-                // close final pick does, or a close decision that could not be recorded (state bit 0)
-                if (a.vrec != nullptr && flagme) flagme = (w.mg[1] & 1u) != 0u || pick_close;
-            }
             if (slot == 0 && valid) {
                 if (a.margin != nullptr) a.margin[a.cw_base + cw] = (mgq == kQSat) ? CUDART_INF_F : (float)mgq * (1.0f / kQScale);
-                if (flagme) {
-                    if (a.cw_state != nullptr) a.cw_state[a.cw_base + cw] = 1;
-                    a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;
-                }
+                if (flagme) a.flag_list[atomicAdd(a.flag_count, 1)] = a.cw_base + cw;
             }
         }
 #pragma unroll 1

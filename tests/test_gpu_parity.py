@@ -562,31 +562,6 @@ def test_strict_mode_equals_the_compiled_reference_at_1dB(torch_cuda, n, K, crc,
     assert np.array_equal(pc.decode_batch_double(llr[:2048].astype(np.float64), L, mode="strict"), want[:2048])
 
 
-@pytest.mark.parametrize("n,K,crc,L,B", [(11, 1024, 16, 32, 1024), (9, 256, 16, 32, 2048), (11, 1024, 0, 20, 512), (10, 512, 8, 32, 512)])
-def test_close_decisions_checked_in_double(torch_cuda, n, K, crc, L, B):
-    """Strict mode, lists 17..32: a close decision between exactly two forks is recorded (both parents' decided bits)
-    and the verify kernel recomputes the two fork metrics in double along those paths. With the threshold opened up to
-    0.01 nearly every codeword records decisions, and the double-precision gap must reproduce the gap the first pass saw
-    to within the fp32 arithmetic's error -- which it only does if the recorded bits, the reconstruction of every
-    partial sum and the layer-parallel LLR evaluation are all right. The decoded words must equal the oracle's."""
-    torch = torch_cuda
-    from polar_b200 import PolarCode, unpack_bits
-    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
-    _, llr = awgn_llrs(port, B, 1.0, seed=808 + n + L)
-    want = port.decode_batch(llr, L, nthreads=os.cpu_count() or 1)
-    pc.set_strict_tau(1e-2)
-    got = unpack_bits(pc.decode_device(torch.from_numpy(llr).cuda(), L, mode="strict").cpu().numpy().view(np.uint32), K)
-    g32, g64, cw = pc.verify_gaps()
-    flagged = pc.last_flagged
-    print("records %d (on %d codewords), second pass on %d codewords, max |double gap - fp32 gap| = %.3g" % (
-        len(g32), len(set(cw.tolist())), flagged, np.abs(g64 - g32).max() if len(g32) else 0.0))
-    assert len(g32) > B // 4
-    assert np.abs(g64 - g32).max() < 2e-4
-    assert np.array_equal(got, want)
-    # host entry point (chunked): same result
-    assert np.array_equal(pc.decode_batch(llr, L, mode="strict"), want)
-
-
 EXACT_KERNEL = [(11, 1024, 16, 32, 96, 1.0), (11, 1024, 0, 1, 200, 1.0), (11, 1024, 16, 4, 128, 1.0), (9, 256, 16, 3, 150, 1.0),
                 (9, 256, 0, 13, 100, 1.0), (12, 2048, 16, 8, 16, 1.5), (13, 4096, 16, 2, 6, 2.0), (8, 128, 8, 32, 100, 1.0),
                 (5, 16, 4, 16, 100, 0.0), (5, 3, 0, 32, 64, 0.0), (3, 4, 0, 1, 33, 1.0), (1, 1, 0, 1, 5, 0.0), (2, 2, 1, 4, 9, 0.0)]
