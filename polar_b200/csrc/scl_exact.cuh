@@ -108,6 +108,7 @@ struct Args {
     unsigned long long gx_stride;// doubles per block
     int B, n, K, crc, L;
     int W;                       // list size rounded up to a power of two (work is spread over W paths x beta)
+    int sm_count;
     int lamS;                    // first layer kept in shared memory
     int big;                     // layers with more than this many (path, beta) items are refreshed by the whole block
     int smem_x_rows, smem_s_rows;
@@ -123,6 +124,10 @@ template <class In>
 __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nt = blockDim.x;
+    // the warp that decodes the leaves ("warp 0" in the comments). Warps go to the SM's four schedulers by their index in
+    // the block, so with several blocks per SM the leaders -- the one busy warp of each block -- are rotated by block,
+    // or they would all queue at the same scheduler (blocks b, b + #SMs, ... tend to share an SM, hence the second term).
+    const bool lead = wib == (int)((blockIdx.x + blockIdx.x / (unsigned)a.sm_count) % (unsigned)(nt >> 5));
     const int n = a.n, N = 1 << n, L = a.L, W = a.W, lamS = a.lamS;
     int wsh = 0;
     while ((1 << wsh) < W) ++wsh;
@@ -152,7 +157,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
         const In* chan = a.llr + (size_t)cw * N;
 
         // per-path state of warp 0 (PolarCode.cpp:250-263: free stack 0..L-1, first path = L-1)
-        bool active = (wib == 0) && (slot == L - 1);
+        bool active = lead && (slot == L - 1);
         double pm = 0;
         uint32_t s_n = 0;
         int stk = slot, sp = L - 1;
@@ -220,13 +225,13 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                     refresh(lam, is_g, tid, nt);
                     if (lam < n && tid < 32) px[(lam - 1) * 32 + tid] = (unsigned char)tid;
                     __syncthreads();
-                } else if (wib == 0) {
+                } else if (lead) {
                     refresh(lam, is_g, lane, 32);
                     if (lam < n) px[(lam - 1) * 32 + lane] = (unsigned char)lane;
                     __syncwarp();
                 }
             }
-            if (wib != 0) continue;                        // the other warps wait at the next leaf with a big layer
+            if (!lead) continue;                           // the other warps wait at the next leaf with a big layer
 
             // ---- leaf decision (warp 0, lane = path) ----
             if ((phi & 31) == 0) frozen_word = a.frozen_words[phi >> 5];
@@ -361,7 +366,7 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
             __syncwarp();
         }
 
-        if (wib == 0) {
+        if (lead) {
             // ---- u-hat of every path: packed polar transform of the re-encoded codeword (layer 0) ----
             uint32_t* D = srow(0, 0) + lane;
             for (int sw = NW >> 1; sw >= 1; sw >>= 1)
