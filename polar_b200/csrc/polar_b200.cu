@@ -997,7 +997,7 @@ int decode_exact(polar_b200_ctx* c, const In* llr, int B, int L, uint32_t* out, 
     a.gx = c->d_ex_gx;
     a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
     a.first_index = cs ? cs->first_index : 0; a.n_ebno = cs ? cs->n_ebno : 1;
-    a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L; a.sm_count = c->sm_count;
+    a.B = B; a.n = n; a.K = c->K; a.crc = c->crc; a.L = L;
     int W = 1; while (W < L) W <<= 1;
     a.W = W;
     a.big = env_int("POLAR_B200_EXACT_BIG", 32);

@@ -108,7 +108,6 @@ struct Args {
     unsigned long long gx_stride;// doubles per block
     int B, n, K, crc, L;
     int W;                       // list size rounded up to a power of two (work is spread over W paths x beta)
-    int sm_count;
     int lamS;                    // first layer kept in shared memory
     int big;                     // layers with more than this many (path, beta) items are refreshed by the whole block
     int smem_x_rows, smem_s_rows;
@@ -124,10 +123,7 @@ template <class In>
 __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5, nt = blockDim.x;
-    // the warp that decodes the leaves ("warp 0" in the comments). Warps go to the SM's four schedulers by their index in
-    // the block, so with several blocks per SM the leaders -- the one busy warp of each block -- are rotated by block,
-    // or they would all queue at the same scheduler (blocks b, b + #SMs, ... tend to share an SM, hence the second term).
-    const bool lead = wib == (int)((blockIdx.x + blockIdx.x / (unsigned)a.sm_count) % (unsigned)(nt >> 5));
+    const bool lead = wib == 0;                  // the warp that decodes the leaves (rotating it per block was measured: no gain)
     const int n = a.n, N = 1 << n, L = a.L, W = a.W, lamS = a.lamS;
     int wsh = 0;
     while ((1 << wsh) < W) ++wsh;
