@@ -213,7 +213,9 @@ int polar_b200_count_errors(polar_b200_ctx* ctx, const uint32_t* info_packed,
  * get_bler_quick keeps doing that on the host.
  *   ebno_db   host, [n_ebno] (n_ebno <= 64); codeword i uses ebno_db[i % n_ebno]
  *   llr       device, [B][N] fp32 out;  truth_packed  device, [B][ceil(K/32)] out (the info bits)
- * K <= 2048 and N <= 8192 (POLAR_B200_E_UNSUPPORTED beyond).
+ * The channel is evaluated in double like the reference (r = a s + sqrt(1/2) z, llr = -4 r a; Box-Muller on 53-bit
+ * uniforms, tails to |z| = 8.5) and rounded to float once. K <= 2048, N <= 8192, at most 32 parity bits
+ * (POLAR_B200_E_UNSUPPORTED beyond).
  */
 int polar_b200_synthesize(polar_b200_ctx* ctx, unsigned long long seed, long long first_index, int B,
                           const double* ebno_db, int n_ebno, float* llr, uint32_t* truth_packed,

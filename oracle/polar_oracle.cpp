@@ -23,6 +23,10 @@
 // (PolarCode.cpp:38-40); reproducing that permutation means calling the same
 // std::sort with the same comparator on the same sequence.
 //
+// Besides the reference's rules it can evaluate two variants that are NOT the reference's (Decoder::minsum_only):
+// min-sum check nodes everywhere (a sensitivity probe) and, on top, the hardware-friendly metric update max(x, 0) --
+// the checker of the product's opt-in MINSUM mode (tests/test_gpu_parity.py::test_minsum_mode_matches_the_minsum_oracle).
+//
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
 // reference legs may load this library.
 #include <algorithm>
