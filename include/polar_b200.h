@@ -84,6 +84,14 @@ int polar_b200_info_words(int K);
 void* polar_b200_host_alloc(size_t bytes, int write_combined);
 int polar_b200_host_free(void* p);
 
+/*
+ * The table of compiled first-pass kernel variants (test hook): entry i serves block length 2^nlog and list sizes in
+ * (2^(lanes_log2 - 1), 2^lanes_log2]; POLAR_B200_FAST_VARIANT=<i> in the environment forces it for matching calls and
+ * POLAR_B200_INFO_KERNEL_KIND then reports 1 + i.
+ */
+int polar_b200_fast_variant_count(void);
+int polar_b200_fast_variant_desc(int index, int* nlog, int* lanes_log2, int* warps_per_block);
+
 /* CUDA devices visible to this process (0 when there is none). */
 int polar_b200_device_count(void);
 

@@ -70,6 +70,8 @@ def dev():
         lib.polar_b200_synthesize.argtypes = [vp, C.c_ulonglong, C.c_longlong, ip, vp, ip, vp, vp, vp]
         lib.polar_b200_bler_sweep.argtypes = [vp, C.c_ulonglong, C.c_longlong, C.c_longlong, vp, ip, vp, ip, ip, vp, vp]
         lib.polar_b200_device_count.restype = ip
+        lib.polar_b200_fast_variant_count.restype = ip
+        lib.polar_b200_fast_variant_desc.argtypes = [ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
         lib.polar_b200_host_alloc.restype = vp
         lib.polar_b200_host_alloc.argtypes = [C.c_size_t, ip]
         lib.polar_b200_host_free.argtypes = [vp]

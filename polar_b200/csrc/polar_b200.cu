@@ -1284,6 +1284,15 @@ int polar_b200_host_free(void* p) {
     return (int)cudaFreeHost(p);
 }
 
+int polar_b200_fast_variant_count(void) { return kNumFastVariants; }
+int polar_b200_fast_variant_desc(int index, int* nlog, int* lanes_log2, int* warps_per_block) {
+    if (index < 0 || index >= kNumFastVariants) return POLAR_B200_E_ARG;
+    if (nlog) *nlog = kFastVariants[index].nlog;
+    if (lanes_log2) *lanes_log2 = kFastVariants[index].wlog;
+    if (warps_per_block) *warps_per_block = kFastVariants[index].wpb;
+    return POLAR_B200_OK;
+}
+
 int polar_b200_device_count(void) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }

@@ -119,6 +119,33 @@ def test_fp32_kernels_alone_match_oracle_on_awgn(torch_cuda, n, K, crc, L, B, eb
     assert mism <= 1, "%d of %d codewords differ from the oracle" % (mism, B)
 
 
+def test_every_compiled_fast_variant(torch_cuda, monkeypatch):
+    """Every entry of the first-pass variant table (defaults and the alternates that only POLAR_B200_FAST_VARIANT selects),
+    forced in turn, decodes a small batch exactly like the oracle -- in fp32 mode (the variant alone) and in strict mode."""
+    import ctypes as C
+    from polar_b200 import PolarCode, _lib
+    lib = _lib.dev()
+    count = lib.polar_b200_fast_variant_count()
+    assert count >= 50
+    seen = set()
+    for i in range(count):
+        nlog, wlog, wpb = C.c_int(), C.c_int(), C.c_int()
+        assert lib.polar_b200_fast_variant_desc(i, C.byref(nlog), C.byref(wlog), C.byref(wpb)) == 0
+        n, L = nlog.value, (1 << wlog.value) - (1 if wlog.value >= 2 else 0)      # 1, 2, 3, 7, 15, 31: fills the lanes, not a power of two
+        K, crc = (1 << n) // 2, 16
+        B = 48 if n <= 11 else 12
+        monkeypatch.setenv("POLAR_B200_FAST_VARIANT", str(i))
+        port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+        _, llr = awgn_llrs(port, B, 1.5, seed=6100 + i)
+        want = port.decode_batch(llr, L, nthreads=os.cpu_count() or 1)
+        got = pc.decode_batch(llr, L, mode="fp32")
+        assert pc.info(6) == 1 + i, "variant %d (n=%d, lanes 2^%d) was not the one that ran" % (i, n, wlog.value)
+        assert np.array_equal(got, want), "variant %d (n=%d, list %d, %d warps per block)" % (i, n, L, wpb.value)
+        assert np.array_equal(pc.decode_batch(llr, L, mode="strict"), want)
+        seen.add((n, wlog.value))
+    assert {(11, 5), (11, 2), (11, 0), (9, 5), (13, 5)} <= seen
+
+
 # lists 33..127 (PolarCode.cpp:497-605 uses uint8_t counters, so 127 is the reference's limit): one codeword per
 # 64- or 128-thread block
 WIDE = [
