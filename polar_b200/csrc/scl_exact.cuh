@@ -92,6 +92,16 @@ __device__ __forceinline__ double softplus_fast(double x, const Tables* t) {
     return fmax(x, 0.0) + log1p_unit(exp_neg(fabs(x), t), t);
 }
 constexpr double kTieMargin = 1e-9;
+__device__ __forceinline__ unsigned long long wmax64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL_MASK, v, o); v = t > v ? t : v; }
+    return v;
+}
+__device__ __forceinline__ unsigned long long wmin64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(FULL_MASK, v, o); v = t < v ? t : v; }
+    return v;
+}
 
 template <class In>
 struct Args {
@@ -261,21 +271,35 @@ __global__ void __launch_bounds__(NT) scl_exact_kernel(const Args<In> a) {
                     }
                 }
                 if (slow) {
-                    // exact rule: keep the rho best of the 2A forks under (metric asc, fork index asc)
-                    // == PolarCode.cpp:528-553 (sort, threshold, '>' pass then '==' pass in index order)
-                    int r0 = 0, r1 = 0;
-                    for (int j = 0; j < W; ++j) {
-                        const double o0 = __shfl_sync(FULL_MASK, m0, j);
-                        const double o1 = __shfl_sync(FULL_MASK, m1, j);
-                        if ((act_g >> j) & 1u) {
-                            r0 += (o0 < m0) || (o0 == m0 && j < slot);
-                            r0 += (o1 < m0) || (o1 == m0 && j < slot);
-                            r1 += (o0 < m1) || (o0 == m1 && j <= slot);
-                            r1 += (o1 < m1) || (o1 == m1 && j < slot);
-                        }
+                    // keep the L best of the 2A forks under (metric asc, fork index asc) == PolarCode.cpp:528-553 (sort,
+                    // threshold, '>' pass then '==' pass in index order): start from "every likely fork", promote the best
+                    // unlikely fork while the list has room, then swap it for the worst kept likely fork while that improves
+                    // the kept set. Metrics are non-negative doubles, so their bit patterns order like the values.
+                    const bool like1 = m1 < m0;                                // likely fork is bit 1
+                    const unsigned long long klo = (unsigned long long)__double_as_longlong(like1 ? m1 : m0);
+                    const unsigned long long khi = (unsigned long long)__double_as_longlong(like1 ? m0 : m1);
+                    const unsigned lk = __ballot_sync(FULL_MASK, like1);
+                    unsigned keptA = act_g, keptB = 0;
+                    int count = A;
+                    while (true) {
+                        const unsigned candB = act_g & ~keptB;
+                        if (candB == 0) break;
+                        const unsigned long long kb = wmin64(((candB >> lane) & 1u) ? khi : ~0ull);
+                        const unsigned eqb = __ballot_sync(FULL_MASK, ((candB >> lane) & 1u) && khi == kb);
+                        const int bl = __ffs(eqb) - 1;                         // lowest lane = lowest fork index among equals
+                        if (count < L) { keptB |= 1u << bl; ++count; continue; }
+                        const unsigned long long ka = wmax64(((keptA >> lane) & 1u) ? klo : 0ull);
+                        const unsigned eqa = __ballot_sync(FULL_MASK, ((keptA >> lane) & 1u) && klo == ka);
+                        const int al = 31 - __clz(eqa);                        // highest lane = highest fork index among equals
+                        const int idxb = 2 * bl + (((lk >> bl) & 1u) ? 0 : 1);
+                        const int idxa = 2 * al + (((lk >> al) & 1u) ? 1 : 0);
+                        if (!((kb < ka) || (kb == ka && idxb < idxa))) break;
+                        keptB |= 1u << bl;
+                        keptA &= ~(1u << al);
                     }
-                    keep0 = active && r0 < L;
-                    keep1 = active && r1 < L;
+                    const bool ka_ = (keptA >> lane) & 1u, kb_ = (keptB >> lane) & 1u;
+                    keep0 = like1 ? kb_ : ka_;
+                    keep1 = like1 ? ka_ : kb_;
                     // margin of this selection: best dropped fork - worst kept fork
                     const double kept = group_max<double>(rmax<double>(keep0 ? m0 : -CUDART_INF, keep1 ? m1 : -CUDART_INF), 32);
                     const double dropped = group_min<double>(rmin<double>((active && !keep0) ? m0 : CUDART_INF,
