@@ -112,7 +112,7 @@ int polar_b200_device_count(void);
  *   crc_matrix   [crc_bits][K] row-major 0/1 (_crc_matrix); may be NULL when crc_bits == 0
  *   max_list     largest list size that will be requested (1..127, the reference's own limit:
  *                its loop counters are uint8_t, PolarCode.cpp:497-605)
- *   max_batch    largest B for the *_host entry points (sizes the staging buffers;
+ *   max_batch    expected largest B of the *_host entry points (initial size of the staging buffers, which grow on demand;
  *                the device-pointer entry points accept any B)
  */
 int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bits,
@@ -177,7 +177,7 @@ int polar_b200_decode_scl_llr_f64_strict_host(polar_b200_ctx* ctx, const double*
  * 505-506) on double LLRs, i.e. the arithmetic of PolarCode::decode_scl_llr itself. For callers that
  * need the reference's decisions on near-tied codewords (arithmetic contract); an
  * order of magnitude slower than the fp32 path (generic kernel, software exp/log).
- *   llr: [B][N] double, device (first form) or host (second form, synchronous, B <= max_batch).
+ *   llr: [B][N] double, device (first form) or host (second form, synchronous; staging grows on demand).
  */
 int polar_b200_decode_scl_llr_f64(polar_b200_ctx* ctx, const double* llr, int B, int L,
                                   uint32_t* info_packed, void* cuda_stream);
@@ -193,7 +193,7 @@ int polar_b200_decode_scl_llr_f64_host(polar_b200_ctx* ctx, const double* llr_ho
  * Evaluated in double with individually rounded products (no FMA contraction), i.e. the reference's own
  * arithmetic. Note the reference's argument order: p1 first.
  *   p1, p0: [B][N] double, P(y_i | 1) and P(y_i | 0) in the reference's channel order; device pointers (first
- *   form, asynchronous on the stream) or host pointers (second form, synchronous, B <= max_batch).
+ *   form, asynchronous on the stream) or host pointers (second form, synchronous; staging grows on demand).
  * The reference's BLER harness never calls this decoder (PolarCode.cpp:755 is commented out); it is provided so
  * that the class surface is complete, on the block-per-codeword kernel (not the throughput path).
  */
