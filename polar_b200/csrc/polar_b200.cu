@@ -1,9 +1,10 @@
 // polar_b200 -- LLR-domain SC / SCL polar decoder for B200 (sm_100a); C ABI in include/polar_b200.h.
 //
-// This file: the generic warp kernel (any n <= 13, any list <= 32, float or double), the error-count and
-// synthetic-front-end kernels, and the C ABI with its dispatch: scl_fast.cuh variants (fast_parts.cu) where one
-// exists for (n, list), scl_wide.cuh for lists 33..127, n = 14, 15 and the probability domain, the generic
-// kernel otherwise.
+// This file: the generic warp kernel (any n <= 13, any list <= 32, float or double; also strict mode's third pass),
+// the error-count and synthetic-front-end kernels, the device-side BLER sweep, the NCCL communicator wrappers, and the
+// C ABI with its dispatch by arithmetic mode: scl_fast.cuh variants (fast_parts.cu) where one exists for (n, list) --
+// followed in STRICT mode by scl_exact.cuh on the flagged codewords --, scl_wide.cuh for lists 33..127, n = 14, 15 and
+// the probability domain, the generic kernel otherwise.
 //
 // What is computed is the reference's decode_scl_llr (PolarC/PolarCode.cpp:130-190,
 // 422-644): Tal-Vardy successive-cancellation list decoding with LLR path metrics,

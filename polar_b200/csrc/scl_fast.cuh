@@ -1,4 +1,4 @@
-// scl_fast.cuh -- the throughput kernel: block lengths 2^8..2^12, list sizes 17..32 with one codeword per warp
+// scl_fast.cuh -- the throughput kernel (STRICT mode's first pass): block lengths 2^8..2^13, list sizes 17..32 with one codeword per warp
 // (lane = list path) and list sizes 1..16 with 2..32 codewords per warp (W = list size rounded up to a power of
 // two lanes per codeword; list 1 = plain SC with lane = codeword).
 //
@@ -27,6 +27,12 @@
 //   * with 16 or 32 codewords per warp (lists 1..2) the channel LLRs and the XS arrays of the warp's codewords
 //     are staged transposed ([position/4][codeword][4], [index][codeword]) so that the lanes of a warp read
 //     neighbouring words (top_solo_transposed);
+//   * path metrics are fixed-point numbers relative to the best path of the list (Q8.24, renormalised every 16 leaves,
+//     saturating): exact additions, keys that feed the warp REDUX directly, no float granularity at metric ~ 700;
+//     plain SC keeps no metric at all;
+//   * every keep/drop decision leaves its margin (best dropped - worst kept metric; |LLR| for plain SC; runner-up gap
+//     of the final pick) and the smallest one per codeword decides whether STRICT mode decodes the codeword again in
+//     double (scl_exact.cuh); the block-error comparison of the BLER loop can be fused into the tail;
 //   * compiled configurations are listed in fast_parts.cu (see fast_variants.cuh); DESIGN.md section 3 has the
 //     placement of every layer and section 5 the measurements behind each choice.
 #pragma once

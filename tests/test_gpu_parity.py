@@ -589,6 +589,28 @@ def test_strict_mode_equals_the_compiled_reference_at_1dB(torch_cuda, n, K, crc,
     assert np.array_equal(pc.decode_batch_double(llr[:2048].astype(np.float64), L, mode="strict"), want[:2048])
 
 
+@pytest.mark.parametrize("n,K,crc,L,B", [(9, 256, 16, 8, 40000), (11, 1024, 16, 32, 12000), (9, 256, 0, 1, 70000)])
+def test_strict_mode_through_the_chunked_host_entry(torch_cuda, n, K, crc, L, B):
+    """The host entry point cuts the batch into chunks that share one flag list (indices offset by the chunk's first
+    codeword) and runs the second pass once after the last chunk. With the threshold opened to 1e-3 every chunk
+    contributes flagged codewords; host and device entry points must agree word for word, and with the oracle on a sample."""
+    torch = torch_cuda
+    from polar_b200 import PolarCode, unpack_bits
+    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+    _, llr = awgn_llrs(port, B, 1.0, seed=4711 + n + L)
+    pc.set_strict_tau(1e-3)
+    host = pc.decode_batch(llr, L, mode="strict")
+    chunks, flagged_host = pc.info(7), pc.last_flagged
+    dev = unpack_bits(pc.decode_device(torch.from_numpy(llr).cuda(), L, mode="strict").cpu().numpy().view(np.uint32), K)
+    flagged_dev = pc.last_flagged
+    print("chunks %d, second pass on %d (host) / %d (device) of %d codewords" % (chunks, flagged_host, flagged_dev, B))
+    assert chunks >= 2 and flagged_host == flagged_dev and flagged_host > B // 200
+    assert np.array_equal(host, dev)
+    S = 1500 if L < 32 else 300
+    idx = np.linspace(0, B - 1, S).astype(int)
+    assert np.array_equal(host[idx], port.decode_batch(llr[idx], L, nthreads=os.cpu_count() or 1))
+
+
 EXACT_KERNEL = [(11, 1024, 16, 32, 96, 1.0), (11, 1024, 0, 1, 200, 1.0), (11, 1024, 16, 4, 128, 1.0), (9, 256, 16, 3, 150, 1.0),
                 (9, 256, 0, 13, 100, 1.0), (12, 2048, 16, 8, 16, 1.5), (13, 4096, 16, 2, 6, 2.0), (8, 128, 8, 32, 100, 1.0),
                 (5, 16, 4, 16, 100, 0.0), (5, 3, 0, 32, 64, 0.0), (3, 4, 0, 1, 33, 1.0), (1, 1, 0, 1, 5, 0.0), (2, 2, 1, 4, 9, 0.0)]
