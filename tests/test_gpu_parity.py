@@ -604,7 +604,7 @@ def test_strict_mode_through_the_chunked_host_entry(torch_cuda, n, K, crc, L, B)
     dev = unpack_bits(pc.decode_device(torch.from_numpy(llr).cuda(), L, mode="strict").cpu().numpy().view(np.uint32), K)
     flagged_dev = pc.last_flagged
     print("chunks %d, second pass on %d (host) / %d (device) of %d codewords" % (chunks, flagged_host, flagged_dev, B))
-    assert chunks >= 2 and flagged_host == flagged_dev and flagged_host > B // 200
+    assert chunks >= 2 and flagged_host == flagged_dev and flagged_host > B // 1000
     assert np.array_equal(host, dev)
     S = 1500 if L < 32 else 300
     idx = np.linspace(0, B - 1, S).astype(int)

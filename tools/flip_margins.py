@@ -13,10 +13,11 @@ settings = [(11, 1024, 16, 32, 1.0, 2 ** 21), (11, 1024, 16, 4, 1.0, 2 ** 22), (
             (9, 256, 16, 32, 1.0, 2 ** 22), (11, 1024, 16, 32, 2.0, 2 ** 20)]
 if len(sys.argv) > 3 and sys.argv[3] == "more":     # other block lengths, list sizes and codes than BASELINE.json's
     settings = [(9, 256, 0, 32, 1.0, 2 ** 21), (10, 512, 16, 32, 1.0, 2 ** 20), (12, 2048, 16, 32, 1.0, 2 ** 19),
-                (13, 4096, 16, 32, 1.5, 2 ** 17), (8, 128, 8, 32, 1.0, 2 ** 21), (11, 1024, 0, 32, 1.0, 2 ** 20),
+                (13, 2048, 16, 32, 1.0, 2 ** 17), (8, 128, 8, 32, 1.0, 2 ** 21), (11, 1024, 0, 32, 1.0, 2 ** 20),
                 (11, 1024, 16, 2, 1.0, 2 ** 21), (11, 1024, 16, 8, 1.0, 2 ** 20), (11, 1024, 16, 16, 1.0, 2 ** 20),
                 (11, 1024, 16, 24, 1.0, 2 ** 19), (11, 512, 16, 32, 0.0, 2 ** 19), (11, 1536, 16, 32, 3.0, 2 ** 19)]
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+settings = settings[int(os.environ.get("FLIP_SKIP", "0")):]
 CH = 65536
 rows = []
 for (n, K, crc, L, eb, total) in settings:
