@@ -1,5 +1,5 @@
 #!/bin/bash
-# round 2, session s: the whole GPU suite again (no -x) and the broader tau campaign (other codes / list sizes)
+# round 2, session s: the broader tau campaign (other codes / block lengths / list sizes than BASELINE.json's)
 mkdir -p gpurun_out
-FLIP_SKIP=3 timeout 700 python tools/flip_margins.py 0.5 gpurun_out/r02s_flip_more2.json more > gpurun_out/r02s_flip_more2.txt 2>&1
-tail -3 gpurun_out/r02s_flip_more2.txt | cut -c1-400
+timeout 800 python tools/flip_margins.py 8 gpurun_out/r02s_flip_more.json more > gpurun_out/r02s_flip_more.txt 2>&1
+tail -3 gpurun_out/r02s_flip_more.txt | cut -c1-300
