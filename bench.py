@@ -386,7 +386,10 @@ def run_ours(args):
         sm_count = code.info(1)
         # the dominant kernel (scl_fast_kernel) alone: in strict / f64 mode the step also holds the second pass, so its
         # launch duration is the fp32 arm's step (the same kernel, one launch per step, timed with CUDA events above)
-        kernel_ms = ms_other if mode in ("strict", "f64") else ms_step
+        # (list size 1 in strict mode runs its own first-pass kernel, sc_ssc_kernel: its duration is the strict step itself,
+        # the second pass behind it being a near-empty launch)
+        ssc = code.info(6) == 500
+        kernel_ms = ms_other if (mode in ("strict", "f64") and not ssc) else ms_step
         achieved = B * bytes_cw / (kernel_ms * 1e-3) / 1e9   # per GPU: one launch decodes this rank's B codewords
         strict_flagged = flagged if mode == "strict" else flagged_other
         out = {
@@ -410,7 +413,7 @@ def run_ours(args):
                          "traffic_source": (traffic_src or {}).get("source"),
                          "traffic_note": "dram bytes/codeword of the committed ncu --set full capture (batch %s) x this batch"
                                          % (traffic_src or {}).get("captured_batch", "16384"),
-                         "kernel": "scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel",
+                         "kernel": "sc_ssc_kernel" if ssc else ("scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel"),
                          "kernel_kind": code.info(6), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step},
             "modes": {mode: value, other: world * B / (ms_other * 1e-3), "unit": "codewords/s (device-resident)",
                       "strict_flagged_per_step": strict_flagged, "strict_flag_rate": strict_flagged / float(world * B),

@@ -92,6 +92,15 @@ int polar_b200_host_free(void* p);
 int polar_b200_fast_variant_count(void);
 int polar_b200_fast_variant_desc(int index, int* nlog, int* lanes_log2, int* warps_per_block);
 
+/*
+ * Test hooks of the list-size-1 first pass of STRICT mode (sc_ssc.cuh: plain SC on the pruned decoding tree, N = 2^8..2^12;
+ * POLAR_B200_SSC=0 in the environment switches it off, POLAR_B200_INFO_KERNEL_KIND reports 500). No GPU needed.
+ * _schedule: the per-code operation list built from frozen_mask ([2^n] bytes); returns its length (0: this code is not
+ * served by that kernel), writes it when cap is large enough. _positions: where output bit j is gathered from, [K].
+ */
+int polar_b200_ssc_schedule(int n, const uint8_t* frozen_mask, uint32_t* ops_out, int cap);
+int polar_b200_ssc_positions(int n, const uint16_t* info_order, int K, uint16_t* pos_out);
+
 /* CUDA devices visible to this process (0 when there is none). */
 int polar_b200_device_count(void);
 
@@ -268,11 +277,10 @@ enum {
     POLAR_B200_INFO_SMEM_BYTES = 4,      /* dynamic shared memory of the last decode launch */
     POLAR_B200_INFO_SCRATCH_BYTES = 5,   /* device scratch owned by the ctx                 */
     POLAR_B200_INFO_KERNEL_KIND = 6,     /* last decode: 0 = generic kernel, 1 + i = fast variant i, -1 = f64 mode,
-                                            1000 + i = min-sum build i, -2 = wide-list kernel (lists 33..127),
+                                            500 = plain SC on the pruned tree, 1000 + i = min-sum build i, -2 = wide-list kernel (lists 33..127),
                                             -3 = wide-list kernel in f64, -4 = probability-domain decoder */
     POLAR_B200_INFO_HOST_CHUNKS = 7,     /* chunks the last *_host call was pipelined in            */
-    POLAR_B200_INFO_LAST_FLAGGED = 8,    /* codewords the last STRICT call decoded again in double (waits for it) */
-    POLAR_B200_INFO_LAST_RECORDED = 9    /* close decisions the last STRICT call checked in double instead (lists 17..32) */
+    POLAR_B200_INFO_LAST_FLAGGED = 8     /* codewords the last STRICT call decoded again in double (waits for it) */
 };
 long long polar_b200_get_info(polar_b200_ctx* ctx, int key);
 

@@ -72,6 +72,8 @@ def dev():
         lib.polar_b200_device_count.restype = ip
         lib.polar_b200_fast_variant_count.restype = ip
         lib.polar_b200_fast_variant_desc.argtypes = [ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
+        lib.polar_b200_ssc_schedule.argtypes = [ip, vp, vp, ip]
+        lib.polar_b200_ssc_positions.argtypes = [ip, vp, ip, vp]
         lib.polar_b200_host_alloc.restype = vp
         lib.polar_b200_host_alloc.argtypes = [C.c_size_t, ip]
         lib.polar_b200_host_free.argtypes = [vp]

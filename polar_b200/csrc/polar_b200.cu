@@ -59,6 +59,7 @@ typedef enum { ncclSum = 0 } ncclRedOp_t;
 
 #include "polar_dev.cuh"
 #include "fast_variants.cuh"
+#include "sc_ssc.cuh"
 #include "scl_wide.cuh"
 #include "scl_exact.cuh"
 
@@ -554,6 +555,11 @@ struct polar_b200_ctx {
     size_t ex_gx_bytes = 0;
     double* d_cvt = nullptr;               // float -> double conversion buffer of the kernels that take one input type
     size_t cvt_bytes = 0;
+    // plain SC on the pruned tree (sc_ssc.cuh), strict mode's first pass at list size 1: per-code schedule and output map
+    uint32_t* d_ssc_sched = nullptr;
+    uint16_t* d_ssc_pos = nullptr;
+    ssc::Layout ssc_lay = {};
+    bool ssc_ok = false, ssc_prepared = false;
     long long last_flagged = -1;           // resolved lazily (device counter)
     bool flagged_pending = false;
     // one call in flight per ctx: every entry point makes its stream wait for the previous call's last launch
@@ -825,6 +831,45 @@ int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_
     return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
+// plain SC on the pruned tree (sc_ssc.cuh): list size 1 with a flag list, i.e. strict mode's first pass -- the rate-1 node
+// shortcut is exact only while every deciding LLR has a trustworthy sign, which the margin / flag list / second pass
+// take care of. One block per SM; 8 codewords per warp.
+int decode_ssc(polar_b200_ctx* c, const float* llr, int B, uint32_t* out, cudaStream_t st, float* margin, int* flag_list,
+               int* flag_count, float tau, int cw_base, const CountSpec* cs) {
+    const ssc::Layout& lay = c->ssc_lay;
+    const int smem = lay.bytes * lay.warps;
+    const bool few = lay.warps <= 8;           // the build for up to 8 warps per SM may use 255 registers per thread
+    if (!c->ssc_prepared) {
+        CU_TRY(few ? cudaFuncSetAttribute(ssc::sc_ssc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
+                   : cudaFuncSetAttribute(ssc::sc_ssc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        c->ssc_prepared = true;
+    }
+    ssc::Args A;
+    memset(&A, 0, sizeof(A));
+    fastcommon::Args& a = A.a;
+    a.llr = llr; a.out = out; a.frozen_words = c->d_frozen; a.info_order = c->d_order; a.crc_masks = c->d_crc_masks;
+    a.B = B; a.K = c->K; a.crc = c->crc; a.L = 1;
+    a.margin = margin; a.flag_list = flag_list; a.flag_count = flag_count; a.cw_base = cw_base;
+    a.truth = cs ? cs->truth : nullptr; a.err = cs ? cs->err : nullptr;
+    a.first_index = cs ? cs->first_index : 0; a.n_ebno = cs ? cs->n_ebno : 1;
+    const double q = (double)tau * 16777216.0;
+    a.tauq_flag = q >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)q;
+    a.tauq = a.tauq_flag; a.tau = tau;
+    A.sched = c->d_ssc_sched; A.pos = c->d_ssc_pos; A.lay = lay;
+    int wpb = env_int("POLAR_B200_SSC_WARPS", lay.warps);
+    if (wpb < 1 || wpb > lay.warps) wpb = lay.warps;
+    int blocks = c->sm_count;
+    const int need = (B + 8 * wpb - 1) / (8 * wpb);
+    if (blocks > need) blocks = need;
+    if (few) ssc::sc_ssc_kernel<8><<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
+    else ssc::sc_ssc_kernel<16><<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
+    CU_TRY(cudaGetLastError());
+    c->launches += 1;
+    c->last_wpb = wpb; c->last_blocks = blocks; c->last_smem = lay.bytes * wpb;
+    c->last_kernel = 500;
+    return POLAR_B200_OK;
+}
+
 // margin (device, [>= cw_base + B], may be null) / flags: see fastcommon::Args. cw_base = index of llr's first row in the caller's
 // batch (the host entry point decodes chunk by chunk but keeps one flag list).
 // variant >= 0: entry of the reference-arithmetic table; variant <= -100: entry -100 - variant of the min-sum table.
@@ -832,6 +877,9 @@ int decode_fast(polar_b200_ctx* c, int variant, const float* llr, int B, int L, 
                 float* margin = nullptr, int* flag_list = nullptr, int* flag_count = nullptr, float tau = 0.0f, int cw_base = 0,
                 const CountSpec* cs = nullptr) {
     const FastVariant& v = variant <= -100 ? kFastMsPart[-100 - variant] : kFastVariants[variant];
+    if (variant >= 0 && v.wlog == 0 && flag_list != nullptr && c->ssc_ok && env_int("POLAR_B200_SSC", 1) != 0 &&
+        env_int("POLAR_B200_FAST_VARIANT", -1) < 0)
+        return decode_ssc(c, llr, B, out, st, margin, flag_list, flag_count, tau, cw_base, cs);
     int blocks = c->sm_count * v.bps;
     const int warps = blocks * v.wpb;
     const size_t need_gx = v.gx_floats * warps * sizeof(float), need_gs = v.gs_words * warps * sizeof(uint32_t);
@@ -1285,6 +1333,23 @@ int polar_b200_host_free(void* p) {
     return (int)cudaFreeHost(p);
 }
 
+// test hook (no GPU needed): the pruned-tree schedule and output map sc_ssc.cuh builds for a code
+int polar_b200_ssc_schedule(int n, const uint8_t* frozen_mask, uint32_t* ops_out, int cap) {
+    if (!frozen_mask || cap < 0) return POLAR_B200_E_ARG;
+    std::vector<uint32_t> ops;
+    if (!ssc::build_schedule(n, frozen_mask, ops)) return 0;
+    if ((int)ops.size() > cap || !ops_out) return (int)ops.size();
+    memcpy(ops_out, ops.data(), ops.size() * 4);
+    return (int)ops.size();
+}
+int polar_b200_ssc_positions(int n, const uint16_t* info_order, int K, uint16_t* pos_out) {
+    if (!info_order || !pos_out || K < 1 || n < 2 || n > 15) return POLAR_B200_E_ARG;
+    std::vector<uint16_t> pos;
+    ssc::build_positions(n, info_order, K, pos);
+    memcpy(pos_out, pos.data(), (size_t)K * 2);
+    return POLAR_B200_OK;
+}
+
 int polar_b200_fast_variant_count(void) { return kNumFastVariants; }
 int polar_b200_fast_variant_desc(int index, int* nlog, int* lanes_log2, int* warps_per_block) {
     if (index < 0 || index >= kNumFastVariants) return POLAR_B200_E_ARG;
@@ -1366,6 +1431,20 @@ int polar_b200_create(polar_b200_ctx** out, int device, int n, int K, int crc_bi
         if ((rc = (int)cudaMemcpy(c->d_inv_order, inv.data(), (size_t)N * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
         if ((rc = (int)cudaMemcpy(c->d_crc_rows, rows.data(), rows.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
     }
+    {
+        // list size 1 in strict mode: schedule of the pruned tree and the output map (sc_ssc.cuh)
+        std::vector<uint32_t> ops;
+        std::vector<uint16_t> pos;
+        if (ssc::build_schedule(n, frozen_mask, ops)) {
+            ssc::build_positions(n, info_order, K, pos);
+            c->ssc_lay = ssc::make_layout(n);
+            if ((rc = (int)cudaMalloc(&c->d_ssc_sched, ops.size() * 4)) != 0) return fail(rc);
+            if ((rc = (int)cudaMalloc(&c->d_ssc_pos, pos.size() * 2)) != 0) return fail(rc);
+            if ((rc = (int)cudaMemcpy(c->d_ssc_sched, ops.data(), ops.size() * 4, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+            if ((rc = (int)cudaMemcpy(c->d_ssc_pos, pos.data(), pos.size() * 2, cudaMemcpyHostToDevice)) != 0) return fail(rc);
+            c->ssc_ok = c->ssc_lay.warps >= 1;
+        }
+    }
     if ((rc = (int)cudaMalloc(&c->d_llr_stage, (size_t)max_batch * N * sizeof(float))) != 0) return fail(rc);
     if ((rc = (int)cudaMalloc(&c->d_out_stage, (size_t)max_batch * c->KW * sizeof(uint32_t))) != 0) return fail(rc);
     *out = c;
@@ -1380,6 +1459,7 @@ int polar_b200_destroy(polar_b200_ctx* c) {
     cudaFree(c->d_gx); cudaFree(c->d_gs); cudaFree(c->d_llr_stage); cudaFree(c->d_out_stage);
     cudaFree(c->d_fgx); cudaFree(c->d_fgs); cudaFree(c->d_llr64_stage); cudaFree(c->d_wgx); cudaFree(c->d_wgs); cudaFree(c->d_prob_stage);
     cudaFree(c->d_flag_list); cudaFree(c->d_flag_count); cudaFree(c->d_cvt); cudaFree(c->d_ex_gx);
+    cudaFree(c->d_ssc_sched); cudaFree(c->d_ssc_pos);
     cudaFree(c->d_sw_llr); cudaFree(c->d_sw_truth); cudaFree(c->d_sw_out); cudaFree(c->d_sw_err);
     cudaFreeHost(c->h_f32); cudaFreeHost(c->h_list); cudaFreeHost(c->h_gather); cudaFreeHost(c->h_out2);
     if (c->ev_last) cudaEventDestroy(c->ev_last);

@@ -643,6 +643,55 @@ def test_block_per_codeword_double_kernel_on_edge_rows(torch_cuda, monkeypatch):
             assert [i for i in bad if i not in LATTICE_ROWS] == [], bad
 
 
+SSC = [(11, 1024, 0, 20011, 1.0), (11, 1024, 16, 7001, 2.0), (9, 256, 0, 9999, 1.0), (8, 128, 8, 5003, 1.5), (10, 300, 8, 3000, 0.5),
+       (12, 2048, 16, 1501, 1.5), (11, 1536, 16, 2500, 3.0), (11, 200, 0, 1000, -2.0), (9, 256, 16, 5, 1.0)]
+
+
+@pytest.mark.parametrize("n,K,crc,B,eb", SSC)
+def test_pruned_tree_sc_kernel(torch_cuda, monkeypatch, n, K, crc, B, eb):
+    """List size 1 in strict mode runs sc_ssc.cuh (kernel kind 500: four lanes per codeword, rate-0 / rate-1 nodes never
+    descended into). Bit-exact against the oracle over ragged batches of several rounds per warp; the same bits as the
+    leaf-by-leaf kernel (POLAR_B200_SSC=0); margins reported; flagged codewords = those below the threshold."""
+    from polar_b200 import PolarCode, unpack_bits
+    torch = torch_cuda
+    port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+    _, llr = awgn_llrs(port, B, eb, seed=515 + n + K)
+    want = port.decode_batch(llr, 1, nthreads=os.cpu_count() or 1)
+    d_llr = torch.from_numpy(llr).cuda()
+    margin = torch.empty(B, dtype=torch.float32, device="cuda")
+    out = pc.decode_device(d_llr, 1, mode="strict", margin=margin)
+    assert pc.info(6) == 500
+    flagged = pc.last_flagged
+    got = unpack_bits(out.cpu().numpy().view(np.uint32), K)
+    assert np.array_equal(got, want), "%d of %d codewords differ from the oracle" % (int((got != want).any(1).sum()), B)
+    m = margin.cpu().numpy().astype(np.float64)
+    assert (m >= 0).all() and np.isfinite(m).all()
+    assert int((np.round(m * 2 ** 24) < int(np.float32(1e-5) * 2.0 ** 24)).sum()) == flagged      # the kernel's fixed-point threshold
+    assert np.array_equal(pc.decode_batch(llr, 1), want)                       # host entry point (chunked)
+    monkeypatch.setenv("POLAR_B200_SSC", "0")
+    old = pc.decode_device(d_llr, 1, mode="strict")
+    assert 1 <= pc.info(6) < 500
+    assert torch.equal(old, out)
+
+
+def test_pruned_tree_sc_kernel_on_ties_and_extremes(torch_cuda):
+    """Zero, tied, huge and lattice LLRs: the rate-1 shortcut is not valid on a zero entry -- the margin is then 0 and
+    strict mode's second pass decodes the codeword leaf by leaf; the result must be the reference's."""
+    from polar_b200 import PolarCode
+    for (n, K, crc) in [(9, 256, 0), (11, 1024, 16)]:
+        port, pc = Port(n, K, 0.32, crc), PolarCode(n, K, 0.32, crc)
+        N = 1 << n
+        rng = np.random.default_rng(5)
+        rows = [np.zeros(N), np.full(N, 3.0), np.full(N, -3.0), np.full(N, 1000.0), np.full(N, -1000.0),
+                rng.integers(-2, 3, N).astype(np.float64), rng.integers(-1, 2, N) * 39.5,
+                np.where(rng.random(N) < 0.5, 0.0, rng.normal(2, 2, N))]
+        llr = np.stack(rows).astype(np.float32)
+        want = port.decode_batch(llr, 1)
+        got = pc.decode_batch(llr, 1)
+        assert pc.info(6) == 500 and pc.last_flagged >= 3
+        assert np.array_equal(got, want)
+
+
 MINSUM = [(11, 1024, 16, 32, 128, 1.5), (11, 1024, 0, 1, 2048, 2.0), (11, 1024, 16, 4, 512, 1.5), (9, 256, 0, 32, 512, 2.0),
           (9, 256, 16, 8, 300, 1.0), (11, 1024, 16, 2, 200, 1.5), (9, 256, 16, 13, 130, 1.0)]
 

@@ -103,3 +103,41 @@ def test_product_sources_do_not_touch_the_oracle():
                     if re.search(r"oracle_lib|libpolar_oracle|libpolar_ref|oracle/_build|kernel_model", txt):
                         bad.append(p)
     assert bad == []
+
+
+SSC_CODES = [(8, 128, 0), (9, 256, 0), (9, 256, 16), (10, 300, 8), (11, 1024, 0), (11, 1024, 16), (11, 1536, 16), (12, 1000, 0)]
+
+
+@pytest.mark.parametrize("n,K,crc", SSC_CODES)
+def test_pruned_tree_schedule_decodes_like_the_oracle(n, K, crc):
+    """sc_ssc.cuh's host side: the schedule and the output map the library builds for a code, interpreted by the numpy
+    model of the kernel (tests/ssc_model.py), decode exactly what the oracle decodes with list size 1."""
+    import ssc_model
+    from oracle_lib import Port, awgn_llrs
+    from polar_b200 import _lib
+    port = Port(n, K, 0.32, crc)
+    con = port.construction()
+    lib = _lib.dev()
+    ops = ssc_model.schedule(lib, n, con["frozen"])
+    assert ops is not None and not ops[-3:].any()
+    pos = ssc_model.positions(lib, n, con["order"], K)
+    kinds = np.bincount(ops & 7, minlength=8)
+    assert kinds[ssc_model.OP_R1] > 0 and kinds[ssc_model.OP_C] > 0
+    B = 192 if n <= 10 else 64
+    for eb in (1.0, 3.0):
+        _, llr = awgn_llrs(port, B, eb, seed=77 + n)
+        got, margin = ssc_model.decode(ops, pos, n, K, llr)
+        want = port.decode_batch(llr, 1)
+        ok = margin > 1e-9          # (a zero / vanishing deciding LLR is what strict mode's second pass is for)
+        assert ok.sum() >= B - 2
+        assert np.array_equal(got[ok], want[ok])
+
+
+def test_pruned_tree_schedule_refuses_what_the_kernel_does_not_serve():
+    from polar_b200 import _lib
+    lib = _lib.dev()
+    fr = np.zeros(1 << 13, np.uint8); fr[:100] = 1
+    assert lib.polar_b200_ssc_schedule(13, fr.ctypes.data, None, 0) == 0       # block length out of range
+    assert lib.polar_b200_ssc_schedule(7, fr.ctypes.data, None, 0) == 0
+    assert lib.polar_b200_ssc_schedule(9, np.zeros(512, np.uint8).ctypes.data, None, 0) == 0   # nothing frozen
+    assert lib.polar_b200_ssc_schedule(9, np.ones(512, np.uint8).ctypes.data, None, 0) == 0    # everything frozen
