@@ -54,12 +54,15 @@ enum {
 /*
  * Arithmetic modes of the LLR-domain decoder.
  *   FP32    the throughput kernels alone: float LLRs, the reference's rules of order, hardware exp2/log2. Decisions
- *           taken on a margin smaller than float rounding can differ from the double reference (measured: 1-2.5 in
- *           10^4 codewords at 1 dB, none at >= 1.5 dB).
+ *           taken on a margin smaller than float rounding can differ from the double reference (measured: about 2 in
+ *           10^6 codewords at 1 dB).
  *   STRICT  FP32, plus: every kernel records the smallest margin (gap between the worst kept and the best dropped
  *           fork metric; |LLR| for list 1; runner-up gap of the final pick) each codeword was decided with, and every
  *           codeword whose margin is below tau (polar_b200_set_strict_tau) is decoded again in double. Block lengths /
  *           lists without a margin-reporting kernel run entirely in double. This is what the drop-in class uses.
+ *           List size 1 at N = 2^8..2^12 runs plain SC on the pruned tree here (sc_ssc.cuh: subtrees without frozen
+ *           leaves are decided by the signs of their root LLRs, which is exact as long as no deciding LLR is within tau
+ *           of zero -- the margin this mode checks anyway).
  *   F64     everything in double with the reference's literal formulas (PolarCode.cpp:438-446, 483, 505-506).
  *   MINSUM  opt-in, NOT the reference's arithmetic: min-sum check nodes everywhere (the
  *           reference's own fallback branch, PolarCode.cpp:442-446) and the hardware-friendly metric update (PM += |LLR|

@@ -838,10 +838,13 @@ int decode_ssc(polar_b200_ctx* c, const float* llr, int B, uint32_t* out, cudaSt
                int* flag_count, float tau, int cw_base, const CountSpec* cs) {
     const ssc::Layout& lay = c->ssc_lay;
     const int smem = lay.bytes * lay.warps;
-    const bool few = lay.warps <= 8;           // the build for up to 8 warps per SM may use 255 registers per thread
+    // builds by warps per SM (the fewer warps, the more registers a thread may use, the deeper the channel prefetch)
+    void (*kern)(const ssc::Args) = lay.warps > 10 ? ssc::sc_ssc_kernel<16, 4>
+                                    : env_int("POLAR_B200_SSC_STAGE", 8) == 4 ? ssc::sc_ssc_kernel<10, 4> : ssc::sc_ssc_kernel<10, 8>;
     if (!c->ssc_prepared) {
-        CU_TRY(few ? cudaFuncSetAttribute(ssc::sc_ssc_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
-                   : cudaFuncSetAttribute(ssc::sc_ssc_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU_TRY(cudaFuncSetAttribute(ssc::sc_ssc_kernel<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU_TRY(cudaFuncSetAttribute(ssc::sc_ssc_kernel<10, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU_TRY(cudaFuncSetAttribute(ssc::sc_ssc_kernel<10, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         c->ssc_prepared = true;
     }
     ssc::Args A;
@@ -856,13 +859,13 @@ int decode_ssc(polar_b200_ctx* c, const float* llr, int B, uint32_t* out, cudaSt
     a.tauq_flag = q >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)q;
     a.tauq = a.tauq_flag; a.tau = tau;
     A.sched = c->d_ssc_sched; A.pos = c->d_ssc_pos; A.lay = lay;
+    A.sync_rounds = env_int("POLAR_B200_SSC_SYNC", 1);
     int wpb = env_int("POLAR_B200_SSC_WARPS", lay.warps);
     if (wpb < 1 || wpb > lay.warps) wpb = lay.warps;
     int blocks = c->sm_count;
     const int need = (B + 8 * wpb - 1) / (8 * wpb);
     if (blocks > need) blocks = need;
-    if (few) ssc::sc_ssc_kernel<8><<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
-    else ssc::sc_ssc_kernel<16><<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
+    kern<<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
     CU_TRY(cudaGetLastError());
     c->launches += 1;
     c->last_wpb = wpb; c->last_blocks = blocks; c->last_smem = lay.bytes * wpb;

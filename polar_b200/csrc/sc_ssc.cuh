@@ -10,10 +10,13 @@
 //     of the next one (:431-451), so a quarter maps onto the same quarter of both children: every f / g / partial-sum
 //     step down to nodes of 8 entries touches lane-private data only, and no synchronisation of any kind is needed.
 //     Nodes of 4 entries (one per lane) are finished with shuffles.
-//   * Layer 0 is the channel row itself (two streaming float4 loads per four check nodes, read twice per codeword),
-//     layer 1 lives in TENSOR MEMORY (tcgen05.st/ld 32x32b: N/8 lane-private columns per warp), layers 2.. in shared
+//   * Layer 0 is the channel row itself and layer 1 is never stored: an entry of layer 2 is computed straight from one
+//     float4 of the channel row (its two layer-1 parents on the fly; the row is streamed four times per codeword, out of
+//     L2). Layer 2 lives in TENSOR MEMORY (tcgen05.st/ld 32x32b: N/16 lane-private columns per warp), layers 3.. in shared
 //     memory as [entry/4][lane][4] (one LDS.128 feeds two nodes, one STS.128 stores four), partial sums as packed
-//     words [word][lane]. 38 KB of shared memory per warp at N = 2048: six warps = 48 codewords per SM.
+//     words [word][lane]. 21 KB of shared memory per warp at N = 2048: ten warps = 80 codewords per SM (with layer 1
+//     stored in tensor memory and layer 2 in shared memory it was six warps, and the kernel is latency-bound: measured
+//     31 % issue utilisation at 1.5 warps per scheduler, profiles/r02_ssc_v1_ncu_summary.txt).
 //   * THE TREE IS PRUNED. With one path there is no path metric, so a subtree whose leaves are all frozen needs no LLR
 //     at all (its bits are 0), and a subtree without frozen leaves is decided by the signs of its root LLRs: successive
 //     cancellation below such a node reproduces exactly those signs -- sign f(a,b) = sign a * sign b, and g adds
@@ -37,19 +40,24 @@ namespace ssc {
 
 enum : uint32_t { OP_END = 0, OP_F = 1, OP_G = 2, OP_G0 = 3, OP_C = 4, OP_R0 = 5, OP_R1 = 6, OP_SUB = 7 };
 // op word: bits 0-2 type, 3-6 m (log2 of the node size: the parent for F / G / G0 / C, the node itself otherwise),
-// 7 side (result slot of the node: 0 = left child of its parent, 1 = right), 12 C: left child is all frozen (its partial
-// sums are zero and were never written), 13 C: right child is all frozen. SUB (a node of 32 entries that has frozen and
+// 7 side (result slot of the node: 0 = left child of its parent, 1 = right), 8-9 for the operations that read layer 1
+// (F / G / G0 / R1 of the root's children): which half of the codeword -- 1 = left (layer 1 = f of the channel pairs),
+// 2 = right (g with the left half's partial sums), 3 = right with an all-frozen left half (g = a + b); 12 C: left child is
+// all frozen (its partial sums are zero and were never written), 13 C: right child is all frozen. The root itself has no
+// F / G: its children compute their layer-1 entries on the fly. SUB (a node of 32 entries that has frozen and
 // unfrozen leaves, finished in registers) is followed by one word holding the frozen pattern of its 32 leaves.
 constexpr uint32_t kSide = 1u << 7, kLeftZero = 1u << 12, kRightZero = 1u << 13;
 constexpr int kNLogMin = 8, kNLogMax = 12;
 
 // ---- host: the schedule of one code ----
-inline void emit_node(const uint8_t* frozen, int lo, int m, uint32_t side, std::vector<uint32_t>& ops) {
+// half: 0 below layer 1; for the root's children 1 / 2 / 3 as above; -1 for the root
+inline void emit_node(const uint8_t* frozen, int lo, int m, uint32_t side, std::vector<uint32_t>& ops, int half) {
     const int M = 1 << m;
+    const uint32_t hb = half > 0 ? (uint32_t)half << 8 : 0u;
     int nf = 0;
     for (int i = 0; i < M; ++i) nf += frozen[lo + i] ? 1 : 0;
     if (nf == M) { ops.push_back(OP_R0 | (uint32_t)m << 3 | side); return; }
-    if (nf == 0) { ops.push_back(OP_R1 | (uint32_t)m << 3 | side); return; }
+    if (nf == 0) { ops.push_back(OP_R1 | (uint32_t)m << 3 | side | hb); return; }
     if (m == 5) {
         uint32_t mask = 0;
         for (int i = 0; i < 32; ++i) mask |= (frozen[lo + i] ? 1u : 0u) << i;
@@ -62,12 +70,12 @@ inline void emit_node(const uint8_t* frozen, int lo, int m, uint32_t side, std::
     for (int i = 0; i < h; ++i) { nl += frozen[lo + i] ? 1 : 0; nr += frozen[lo + h + i] ? 1 : 0; }
     const bool left_zero = nl == h, right_zero = nr == h;
     if (!left_zero) {
-        ops.push_back(OP_F | (uint32_t)m << 3);
-        emit_node(frozen, lo, m - 1, 0u, ops);
+        if (half >= 0) ops.push_back(OP_F | (uint32_t)m << 3 | hb);
+        emit_node(frozen, lo, m - 1, 0u, ops, half < 0 ? 1 : 0);
     }
     if (!right_zero) {
-        ops.push_back((left_zero ? OP_G0 : OP_G) | (uint32_t)m << 3);
-        emit_node(frozen, lo + h, m - 1, kSide, ops);
+        if (half >= 0) ops.push_back((left_zero ? OP_G0 : OP_G) | (uint32_t)m << 3 | hb);
+        emit_node(frozen, lo + h, m - 1, kSide, ops, half < 0 ? (left_zero ? 3 : 2) : 0);
     }
     ops.push_back(OP_C | (uint32_t)m << 3 | side | (left_zero ? kLeftZero : 0u) | (right_zero ? kRightZero : 0u));
 }
@@ -81,7 +89,7 @@ inline bool build_schedule(int n, const uint8_t* frozen, std::vector<uint32_t>& 
     int nf = 0;
     for (int i = 0; i < N; ++i) nf += frozen[i] ? 1 : 0;
     if (nf == 0 || nf == N) return false;
-    emit_node(frozen, 0, n, 0u, ops);
+    emit_node(frozen, 0, n, 0u, ops, -1);
     for (int i = 0; i < 3; ++i) ops.push_back(OP_END);          // the interpreter reads two words ahead
     return true;
 }
@@ -101,7 +109,7 @@ inline void build_positions(int n, const uint16_t* order, int K, std::vector<uin
 // ---- layout of one warp's shared memory ----
 struct Layout {
     int n;
-    int x_rows4;          // float4 rows ([lane][4] floats, 512 bytes) of the LLR layers 2 .. n-2
+    int x_rows4;          // float4 rows ([lane][4] floats, 512 bytes) of the LLR layers 3 .. n-5
     int s_rows;           // word rows (128 bytes) of the partial-sum slots of layers 1 .. n-2
     int xrow[16];         // word row of layer lam's left slot (the right slot follows it)
     int bytes;            // per warp
@@ -111,7 +119,7 @@ inline Layout make_layout(int n) {
     Layout l{};
     l.n = n;
     const int N = 1 << n;
-    l.x_rows4 = N / 32 + 1;        // layers with >= 4 entries per lane: N/32 - 1 rows; the 2- and 1-entry layers: one row each
+    l.x_rows4 = N / 64 < 2 ? 2 : N / 64;   // layers 3 .. n-5 (N/32 .. 8 entries per lane): N/64 - 2 rows
     int row = 0;
     for (int lam = 1; lam <= n - 2; ++lam) {
         l.xrow[lam] = row;
@@ -121,7 +129,7 @@ inline Layout make_layout(int n) {
     l.s_rows = row;
     l.bytes = l.x_rows4 * 512 + l.s_rows * 128;
     int w = (227 * 1024 - 1024) / l.bytes;
-    const int tm_cols = N / 8;                       // tensor-memory columns of layer 1 per warp; 512 per lane quadrant
+    const int tm_cols = N / 16;                      // tensor-memory columns of layer 2 per warp; 512 per lane quadrant
     const int tm_warps = 4 * (512 / tm_cols);
     if (w > tm_warps) w = tm_warps;
     if (w > 16) w = 16;
@@ -134,6 +142,7 @@ struct Args {
     const uint32_t* sched;
     const uint16_t* pos;
     Layout lay;
+    int sync_rounds;      // block barrier at the start of every round
 };
 
 #ifdef __CUDACC__
@@ -163,11 +172,20 @@ __device__ __forceinline__ uint32_t spread16(uint32_t x) {
 }
 __device__ __forceinline__ uint32_t interleave16(uint32_t a, uint32_t b) { return spread16(a & 0xFFFFu) | (spread16(b & 0xFFFFu) << 1); }
 
+// the same for H + H -> 2H bits, H <= 4 (inputs hold nothing above bit H-1)
+template <int H>
+__device__ __forceinline__ uint32_t interleave_small(uint32_t a, uint32_t b) {
+    uint32_t x = a | (b << 16);
+    if constexpr (H > 2) x = (x | (x << 2)) & 0x33333333u;
+    if constexpr (H > 1) x = (x | (x << 1)) & 0x55555555u;
+    return (x & 0xFFFFu) | ((x >> 16) << 1);
+}
+
 __device__ __forceinline__ void note(uint32_t& mg, float x) { mg = min(mg, __float_as_uint(fabsf(x))); }
 
-// float offset (within the warp's LLR area, before adding 4 * lane) of layer lam, 2 <= lam <= n-5: [entry / 4][lane][4];
-// sum_{mu=2}^{lam-1} cnt(mu)/4 = N/32 - cnt(lam)/2 rows of 128 floats lie before it
-__device__ __forceinline__ int x_base(int n, int lam) { return ((1 << (n - 5)) - (1 << (n - lam - 3))) * 128; }
+// float offset (within the warp's LLR area, before adding 4 * lane) of layer lam, 3 <= lam <= n-5: [entry / 4][lane][4];
+// sum_{mu=3}^{lam-1} cnt(mu)/4 = N/64 - cnt(lam)/2 rows of 128 floats lie before it
+__device__ __forceinline__ int x_base(int n, int lam) { return ((1 << (n - 6)) - (1 << (n - lam - 3))) * 128; }
 
 // four children from eight consecutive parent entries (two float4): child e = f or g of entries (2e, 2e+1)
 template <bool ISG>
@@ -176,42 +194,55 @@ __device__ __forceinline__ void four(const float4& v0, const float4& v1, uint32_
     node4<ISG>(pa, pb, word, pos, y);
 }
 
+// the two layer-1 entries that one float4 of the channel row yields (PolarCode.cpp:431-451 applied to layer 0): left half
+// of the codeword f, right half g with the left half's partial sums (bits k, k+1 of ab; ab = 0 when that half is all frozen)
+__device__ __forceinline__ void layer1_pair(int half, const float4& v, uint32_t ab, int k, float& e0, float& e1) {
+    if (half == 1) POLAR_FAST_NS::f_rule2(v.x, v.y, v.z, v.w, e0, e1);
+    else POLAR_FAST_NS::g_top2(v.x, v.y, ab << (31 - k), v.z, v.w, ab << (30 - k), e0, e1);
+}
+
 // ---- child LLRs of a node: entry j = f or g of the parent's entries (2j, 2j+1) (PolarCode.cpp:431-451); cnt = entries
 // per lane of the child (>= 8). has_bits = false: every partial sum of the left child is 0 (it is all frozen). Loads run
-// one stage ahead of the arithmetic: with six warps per SM there is little else to hide their latency behind. ----
-template <bool ISG>
-__device__ __forceinline__ void child_llrs(int n, int lam, int cnt, bool has_bits, const float4* chan, uint32_t tm, float* X,
-                                           const uint32_t* sw) {
+// one stage ahead of the arithmetic: with ten warps per SM there is little else to hide their latency behind. ----
+template <bool ISG, int ST>
+__device__ __forceinline__ void child_llrs(int n, int lam, int cnt, bool has_bits, int half, const float4* chan, uint32_t tm,
+                                           float* X, const uint32_t* sw, const uint32_t* sa) {
     uint32_t word = 0;
-    if (lam == 0) {
-        // channel row -> tensor memory, 16 children (8 float4 = 128 bytes of the row) per stage
-        float4 buf[8];
+    if (lam == 1) {
+        // channel row -> (layer 1 on the fly) -> layer 2 in tensor memory: child j comes from float4 j of the lane's quarter;
+        // ST children per stage, the next stage's loads issued before this stage's arithmetic
+        float4 buf[ST];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) buf[k] = __ldg(chan + k);
+        for (int k = 0; k < ST; ++k) buf[k] = __ldg(chan + k);
+        uint32_t aw = 0;
 #pragma unroll 1
-        for (int j = 0; j < cnt; j += 16) {
-            float4 nx[8];
-            const bool more = j + 16 < cnt;
+        for (int j = 0; j < cnt; j += ST) {
+            float4 nx[ST];
+            const bool more = j + ST < cnt;
             if (more) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) nx[k] = __ldg(chan + (j >> 1) + 8 + k);
+                for (int k = 0; k < ST; ++k) nx[k] = __ldg(chan + j + ST + k);
             }
             if (ISG && has_bits && (j & 31) == 0) word = sw[(j >> 5) * 32];
+            if (half == 2 && (j & 15) == 0) aw = sa[(j >> 4) * 32];      // layer-1 entries 2j .. 2j+31 of this lane
 #pragma unroll
-            for (int h = 0; h < 4; ++h) {
-                float y[4];
-                four<ISG>(buf[2 * h], buf[2 * h + 1], word, (j + 4 * h) & 31, y);
-                tm_st4(tm + j + 4 * h, y);
+            for (int h = 0; h < ST; h += 4) {
+                const uint32_t ab = aw >> ((2 * (j + h)) & 31);
+                float pa[4], pb[4], y[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) layer1_pair(half, buf[h + e], ab, 2 * e, pa[e], pb[e]);
+                node4<ISG>(pa, pb, word, (j + h) & 31, y);
+                tm_st4(tm + j + h, y);
             }
             if (more) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) buf[k] = nx[k];
+                for (int k = 0; k < ST; ++k) buf[k] = nx[k];
             }
         }
         tm_wait_st();
-    } else if (lam == 1) {
-        // tensor memory -> shared memory (layer 2), 8 children (16 columns) per stage, two register sets in turn
-        float* dst = X + x_base(n, 2);
+    } else if (lam == 2) {
+        // tensor memory -> shared memory (layer 3), 8 children (16 columns) per stage, two register sets in turn
+        float* dst = X + x_base(n, 3);
         float va[4][4], vb[4][4];
         auto load = [&](float (&v)[4][4], int j) {
 #pragma unroll
@@ -232,11 +263,14 @@ __device__ __forceinline__ void child_llrs(int n, int lam, int cnt, bool has_bit
         for (int j = 0; j < cnt; j += 16) {
             if (ISG && has_bits && (j & 31) == 0) word = sw[(j >> 5) * 32];
             tm_wait_ld16(va);
-            load(vb, j + 8);
+            const bool second = j + 8 < cnt;
+            if (second) load(vb, j + 8);
             work(va, j);
-            tm_wait_ld16(vb);
-            if (j + 16 < cnt) load(va, j + 16);
-            work(vb, j + 8);
+            if (second) {
+                tm_wait_ld16(vb);
+                if (j + 16 < cnt) load(va, j + 16);
+                work(vb, j + 8);
+            }
         }
     } else {
         const float* src = X + x_base(n, lam);
@@ -322,11 +356,13 @@ __device__ __forceinline__ uint32_t sub_node(const float (&a)[E], uint32_t fm, u
             for (int j = 0; j < H; ++j) r[j] = POLAR_FAST_NS::g_rule(a[2 * j], a[2 * j + 1], (xl >> j) & 1u);
             xr = sub_node<H>(r, fr, mg, q);
         }
-        return interleave16(xl ^ xr, xr);
+        return interleave_small<H>(xl ^ xr, xr);
     }
 }
 
-template <int MAXW>
+// MAXW: most warps per block this build is launched with (the fewer, the more registers per thread); ST: channel float4s
+// per prefetch stage of the top operations (4 or 8)
+template <int MAXW, int ST>
 __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ uint32_t tm_base;
@@ -346,12 +382,20 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tm = tm_base + ((uint32_t)((wib & 3) * 32) << 16) + (uint32_t)((wib >> 2) * (N >> 3));
+    const uint32_t tm = tm_base + ((uint32_t)((wib & 3) * 32) << 16) + (uint32_t)((wib >> 2) * (N >> 4));
 
     const int KW = (a.K + 31) >> 5;
     const int groups = (a.B + 7) >> 3;
     const int total_warps = gridDim.x * WPB;
-    for (int grp = blockIdx.x * WPB + wib; grp < groups; grp += total_warps) {
+    // Every warp runs the same number of rounds and the warps of a block start each round together: they then walk through
+    // the same code at about the same time and share the instruction caches (the walk is identical for every codeword).
+    // Unsynchronised, ten warps drift apart over the rounds and instruction fetch becomes the largest stall (measured:
+    // 26 M codewords/s at 22 rounds against 33 M at 6).
+    const int rounds = (groups + total_warps - 1) / total_warps;
+    for (int rnd = 0; rnd < rounds; ++rnd) {
+        const int grp = rnd * total_warps + blockIdx.x * WPB + wib;
+        if (A.sync_rounds) __syncthreads();
+        if (grp >= groups) continue;
         const int cw = grp * 8 + cwl;
         const bool valid = cw < a.B;
         const float4* chan = reinterpret_cast<const float4*>(a.llr + (size_t)(valid ? cw : a.B - 1) * N + (size_t)q * (N >> 2));
@@ -369,8 +413,10 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
             if (type <= OP_G0) {
                 const int cnt = 1 << (m - 3);
                 const uint32_t* sw = S + A.lay.xrow[lam + 1] * 32;      // left child's partial sums
-                if (type == OP_F) child_llrs<false>(n, lam, cnt, false, chan, tm, X, sw);
-                else child_llrs<true>(n, lam, cnt, type == OP_G, chan, tm, X, sw);
+                const uint32_t* sa = S + A.lay.xrow[1] * 32;            // partial sums of the left half of the codeword
+                const int half = (int)((op >> 8) & 3u);
+                if (type == OP_F) child_llrs<false, ST>(n, lam, cnt, false, half, chan, tm, X, sw, sa);
+                else child_llrs<true, ST>(n, lam, cnt, type == OP_G, half, chan, tm, X, sw, sa);
             } else if (type == OP_C) {
                 // partial sums of the parent: entry 2j = left[j] ^ right[j], entry 2j+1 = right[j] (:463-468)
                 const int cl = 1 << (m - 3);         // bits per lane of each child (>= 8)
@@ -379,6 +425,9 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
                 const uint32_t* sr = sl + wc * 32;
                 uint32_t* out = (lam == 0) ? R : S + (A.lay.xrow[lam] + side * (cl >= 16 ? cl >> 4 : 1)) * 32;
                 const bool lz = (op & kLeftZero) != 0, rz = (op & kRightZero) != 0;
+                // the root's partial sums go to the start of the LLR area as [word][lane] rows, which cuts across the other
+                // lanes' [lane][4] LLR slots: every lane must be done reading LLRs first
+                if (lam == 0) __syncwarp();
 #pragma unroll 1
                 for (int w = 0; w < wc; ++w) {
                     const uint32_t r = rz ? 0u : sr[w * 32];
@@ -402,6 +451,23 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
                 uint32_t* out = S + (A.lay.xrow[lam] + side * wc) * 32;
                 uint32_t word = 0;
                 if (lam == 1) {
+                    // a whole half of the codeword without a frozen leaf: its layer-1 entries on the fly
+                    const int half = (int)((op >> 8) & 3u);
+                    const uint32_t* sa = S + A.lay.xrow[1] * 32;
+                    uint32_t aw = 0;
+#pragma unroll 1
+                    for (int j = 0; j < cnt; j += 4) {
+                        const float4 c0 = __ldg(chan + (j >> 1)), c1 = __ldg(chan + (j >> 1) + 1);
+                        if (half == 2 && (j & 31) == 0) aw = sa[(j >> 5) * 32];
+                        const uint32_t ab = aw >> (j & 31);
+                        float v[4];
+                        layer1_pair(half, c0, ab, 0, v[0], v[1]);
+                        layer1_pair(half, c1, ab, 2, v[2], v[3]);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) { note(mg, v[e]); word |= (v[e] < 0.0f ? 1u : 0u) << ((j + e) & 31); }
+                        if (((j + 4) & 31) == 0) { out[(j >> 5) * 32] = word; word = 0; }
+                    }
+                } else if (lam == 2) {
 #pragma unroll 1
                     for (int j = 0; j < cnt; j += 4) {
                         float v[4];
@@ -475,11 +541,16 @@ __global__ void __launch_bounds__(MAXW * 32, 1) sc_ssc_kernel(const Args A) {
             const int jmax = min(32, a.K - 32 * t);
             const uint16_t* pp = A.pos + 32 * t;
             uint32_t word = 0;
-#pragma unroll 8
-            for (int i = 0; i < 32; ++i) {
-                const uint32_t e = __ldg(pp + i);
-                const uint32_t v = Y[(e >> 7) * 32 + ((e >> 5) & 3u)];
-                if (i < jmax) word |= ((v >> (e & 31u)) & 1u) << i;
+#pragma unroll
+            for (int i8 = 0; i8 < 4; ++i8) {
+                const uint4 p8 = __ldg(reinterpret_cast<const uint4*>(pp) + i8);          // eight 16-bit entries
+                const uint32_t pw[4] = {p8.x, p8.y, p8.z, p8.w};
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t e = (pw[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                    const uint32_t v = Y[(e >> 7) * 32 + ((e >> 5) & 3u)];
+                    if (8 * i8 + k < jmax) word |= ((v >> (e & 31u)) & 1u) << (8 * i8 + k);
+                }
             }
             if (valid) {
                 if (a.out != nullptr) a.out[(size_t)cw * KW + t] = word;

@@ -110,8 +110,13 @@ def decode(ops, pos, n, K, llr):
         lam = n - m
         if t == OP_END:
             break
+        if t in (OP_F, OP_G, OP_G0, OP_R1) and lam == 1:
+            # layer 1 is never stored: the root's children compute it from the channel row on the fly
+            half = (op >> 8) & 3
+            c0, c1 = X[0][:, :, 0::2], X[0][:, :, 1::2]
+            X[1] = {1: lambda: f_ref(c0, c1), 2: lambda: g_ref(c0, c1, S[(1, 0)].astype(np.float64)), 3: lambda: c0 + c1}[half]()
         if t in (OP_F, OP_G, OP_G0):
-            assert m >= 6
+            assert 6 <= m < n
             src = X[lam]
             a, b = src[:, :, 0::2], src[:, :, 1::2]
             if t == OP_F:

@@ -2,7 +2,7 @@
 1.0 dB with the fp32 kernels (recording decision margins) and with the GPU's double-precision mode -- which equals the
 CPU reference on every comparison made so far -- and prints the margins of the codewords that differ, next to the share
 of codewords each threshold tau would flag. This is the evidence behind POLAR_B200_DEFAULT_STRICT_TAU.
-usage: python tools/flip_margins.py [scale] [out.json]"""
+usage: python tools/flip_margins.py [scale] [out.json] [more | sc]   (more: twelve other codes / lists; sc: list size 1 on sc_ssc.cuh)"""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
@@ -16,6 +16,10 @@ if len(sys.argv) > 3 and sys.argv[3] == "more":     # other block lengths, list 
                 (13, 2048, 16, 32, 1.0, 2 ** 17), (8, 128, 8, 32, 1.0, 2 ** 21), (11, 1024, 0, 32, 1.0, 2 ** 20),
                 (11, 1024, 16, 2, 1.0, 2 ** 21), (11, 1024, 16, 8, 1.0, 2 ** 20), (11, 1024, 16, 16, 1.0, 2 ** 20),
                 (11, 1024, 16, 24, 1.0, 2 ** 19), (11, 512, 16, 32, 0.0, 2 ** 19), (11, 1536, 16, 32, 3.0, 2 ** 19)]
+SC = len(sys.argv) > 3 and sys.argv[3] == "sc"
+if SC:      # list size 1 on the pruned tree (sc_ssc.cuh): the first arm is that kernel without a second pass (tau -> 0)
+    settings = [(11, 1024, 0, 1, 1.0, 2 ** 23), (11, 1024, 16, 1, 2.0, 2 ** 23), (9, 256, 0, 1, 1.0, 2 ** 24), (10, 300, 8, 1, 0.0, 2 ** 23),
+                (12, 2048, 16, 1, 1.5, 2 ** 22), (8, 128, 8, 1, 1.0, 2 ** 24), (11, 1536, 16, 1, 3.0, 2 ** 23), (11, 512, 16, 1, 0.0, 2 ** 23)]
 scale = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
 settings = settings[int(os.environ.get("FLIP_SKIP", "0")):]
 CH = 65536
@@ -29,7 +33,13 @@ for (n, K, crc, L, eb, total) in settings:
     t0 = time.time()
     for first in range(0, total, CH):
         llr, truth = pc.synthesize(CH, [eb], seed=991, first_index=first)
-        o32 = pc.decode_device(llr, L, mode="fp32", margin=margin)
+        if SC:
+            pc.set_strict_tau(1e-30)
+            o32 = pc.decode_device(llr, L, mode="strict", margin=margin).clone()
+            assert pc.info(6) == 500
+            pc.set_strict_tau(1e-5)
+        else:
+            o32 = pc.decode_device(llr, L, mode="fp32", margin=margin)
         o64 = pc.decode_device(llr, L, mode="f64")
         ost = pc.decode_device(llr, L, mode="strict")
         strict_flagged += pc.last_flagged

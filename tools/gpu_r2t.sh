@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 tail -5 gpurun_out/r02t_pytest_ssc.txt
 {
 export POLAR_B200_STRICT_TAU=1e-30
-for w in 6 4; do echo "warps $w:"; POLAR_B200_SSC_WARPS=$w timeout 120 python tools/list_rate.py 11 1024 0 1 65536 1.5; done
+for w in 10 8 6; do echo "warps $w:"; POLAR_B200_SSC_WARPS=$w timeout 120 python tools/list_rate.py 11 1024 0 1 65536 1.5; done
 POLAR_B200_SSC=0 timeout 120 python tools/list_rate.py 11 1024 0 1 65536 1.5
 timeout 120 python tools/list_rate.py 11 1024 0 1 262144 1.5
 POLAR_B200_SSC=0 timeout 120 python tools/list_rate.py 11 1024 0 1 262144 1.5

@@ -6,7 +6,7 @@ import numpy as np
 from oracle_lib import Port, awgn_llrs
 from polar_b200 import PolarCode
 ok = True
-for (n,K,crc,L,B) in [(9,256,16,32,6),(9,256,16,4,19),(9,256,0,16,5),(11,1024,16,32,3),(11,1024,16,8,9),(7,64,8,3,21),(9,256,0,1,40),(8,128,8,32,4)]:
+for (n,K,crc,L,B) in [(9,256,16,32,6),(9,256,16,4,19),(9,256,0,16,5),(11,1024,16,32,3),(11,1024,16,8,9),(7,64,8,3,21),(9,256,0,1,40),(8,128,8,32,4),(11,1024,16,1,21),(12,2048,0,1,9),(8,128,8,1,50)]:
     port = Port(n,K,0.32,crc); pc = PolarCode(n,K,0.32,crc)
     info, llr = awgn_llrs(port, B, 1.5, 5)
     want = port.decode_batch(llr, L)
