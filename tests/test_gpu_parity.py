@@ -644,7 +644,9 @@ def test_block_per_codeword_double_kernel_on_edge_rows(torch_cuda, monkeypatch):
 
 
 SSC = [(11, 1024, 0, 20011, 1.0), (11, 1024, 16, 7001, 2.0), (9, 256, 0, 9999, 1.0), (8, 128, 8, 5003, 1.5), (10, 300, 8, 3000, 0.5),
-       (12, 2048, 16, 1501, 1.5), (11, 1536, 16, 2500, 3.0), (11, 200, 0, 1000, -2.0), (9, 256, 16, 5, 1.0)]
+       (12, 2048, 16, 1501, 1.5), (11, 1536, 16, 2500, 3.0), (11, 200, 0, 1000, -2.0), (9, 256, 16, 5, 1.0),
+       (9, 3, 0, 700, -6.0), (8, 1, 0, 300, -3.0), (10, 1000, 0, 900, 7.0), (11, 2000, 16, 600, 8.0), (9, 500, 8, 1200, 7.0),
+       (12, 4000, 0, 300, 8.0)]      # halves of the codeword without a frozen / without an unfrozen leaf
 
 
 @pytest.mark.parametrize("n,K,crc,B,eb", SSC)
