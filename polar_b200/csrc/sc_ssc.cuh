@@ -9,7 +9,7 @@
 //     quarters; lane q owns entries [q M/4, (q+1) M/4). The reference pairs entries (2b, 2b+1) of a layer into entry b
 //     of the next one (:431-451), so a quarter maps onto the same quarter of both children: every f / g / partial-sum
 //     step down to nodes of 8 entries touches lane-private data only, and no synchronisation of any kind is needed.
-//     Nodes of 4 entries (one per lane) are finished with shuffles.
+//     Nodes of 32 entries and below are finished in registers (sub_node), those of 4 entries (one per lane) with shuffles.
 //   * Layer 0 is the channel row itself and layer 1 is never stored: an entry of layer 2 is computed straight from one
 //     float4 of the channel row (its two layer-1 parents on the fly; the row is streamed four times per codeword, out of
 //     L2). Layer 2 lives in TENSOR MEMORY (tcgen05.st/ld 32x32b: N/16 lane-private columns per warp), layers 3.. in shared
@@ -25,10 +25,14 @@
 //     sign is in doubt -- which is what STRICT mode's margin is for: the smallest |LLR| over every entry that decided a
 //     bit is the codeword's margin, and a codeword below tau is decoded again by the double-precision second pass,
 //     leaf by leaf. This kernel is therefore used in STRICT mode only; FP32 mode keeps the leaf-by-leaf kernel.
-//     At N = 2048, K = 1024: 6 370 check nodes instead of 11 264, 227 + 101 visited nodes instead of 4 095.
+//     At N = 2048, K = 1024: 6 370 check nodes instead of 11 264 (+ 1 024 for the layer-1 entries that are computed
+//     twice), 328 visited nodes instead of 4 095.
 //   * The walk over the tree is a per-code SCHEDULE built once on the host (build_schedule): a few hundred 32-bit
 //     operations that every lane of every warp interprets in lock step (no divergence: the frozen set is the same for
-//     every codeword).
+//     every codeword). The warps of a block start every round of 8 codewords together (block barrier): they then share
+//     the instruction caches instead of evicting each other's code.
+//   * Measured on B200: N = 2048, K = 1024: 41.7 / 43.5 M codewords/s at batch 65 536 / 262 144
+//     against 27.1 / 25.4 M for the leaf-by-leaf kernel; 13.5 KB of DRAM traffic per codeword (algorithmic: 8.3 KB).
 //
 // Arithmetic: fast::f_rule2 / g_top2 (scl_fast.cuh), i.e. the same fp32 check / variable node as every other fp32 kernel.
 #pragma once
