@@ -302,6 +302,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop()
     launches = code.kernel_launches - launches0
+    kernel_kind = code.info(6)             # first-pass kernel of the timed region
     flagged = code.last_flagged if mode == "strict" else 0
     code.count_errors(d_out, d_truth, d_berr, None)
     torch.cuda.synchronize(dev)
@@ -388,7 +389,7 @@ def run_ours(args):
         # launch duration is the fp32 arm's step (the same kernel, one launch per step, timed with CUDA events above)
         # (list size 1 in strict mode runs its own first-pass kernel, sc_ssc_kernel: its duration is the strict step itself,
         # the second pass behind it being a near-empty launch)
-        ssc = code.info(6) == 500
+        ssc = kernel_kind == 500
         kernel_ms = ms_other if (mode in ("strict", "f64") and not ssc) else ms_step
         achieved = B * bytes_cw / (kernel_ms * 1e-3) / 1e9   # per GPU: one launch decodes this rank's B codewords
         strict_flagged = flagged if mode == "strict" else flagged_other
@@ -413,8 +414,8 @@ def run_ours(args):
                          "traffic_source": (traffic_src or {}).get("source"),
                          "traffic_note": "dram bytes/codeword of the committed ncu --set full capture (batch %s) x this batch"
                                          % (traffic_src or {}).get("captured_batch", "16384"),
-                         "kernel": "sc_ssc_kernel" if ssc else ("scl_fast_kernel" if code.info(6) > 0 else "scl_decode_kernel"),
-                         "kernel_kind": code.info(6), "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step},
+                         "kernel": "sc_ssc_kernel" if ssc else ("scl_fast_kernel" if kernel_kind > 0 else "scl_decode_kernel"),
+                         "kernel_kind": kernel_kind, "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_step},
             "modes": {mode: value, other: world * B / (ms_other * 1e-3), "unit": "codewords/s (device-resident)",
                       "strict_flagged_per_step": strict_flagged, "strict_flag_rate": strict_flagged / float(world * B),
                       "codewords_differing_between_modes": differs_between_modes},

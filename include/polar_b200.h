@@ -60,9 +60,10 @@ enum {
  *           fork metric; |LLR| for list 1; runner-up gap of the final pick) each codeword was decided with, and every
  *           codeword whose margin is below tau (polar_b200_set_strict_tau) is decoded again in double. Block lengths /
  *           lists without a margin-reporting kernel run entirely in double. This is what the drop-in class uses.
- *           List size 1 at N = 2^8..2^12 runs plain SC on the pruned tree here (sc_ssc.cuh: subtrees without frozen
- *           leaves are decided by the signs of their root LLRs, which is exact as long as no deciding LLR is within tau
- *           of zero -- the margin this mode checks anyway).
+ *           List size 1 at N = 2^8..2^12 runs plain SC on the pruned tree (sc_ssc.cuh: subtrees without frozen leaves
+ *           are decided by the signs of their root LLRs, which is exact as long as no deciding LLR is within tau of
+ *           zero -- the margin this mode checks anyway; FP32 mode uses the same kernel and decodes the codewords with
+ *           an exactly-zero deciding LLR leaf by leaf in fp32).
  *   F64     everything in double with the reference's literal formulas (PolarCode.cpp:438-446, 483, 505-506).
  *   MINSUM  opt-in, NOT the reference's arithmetic: min-sum check nodes everywhere (the
  *           reference's own fallback branch, PolarCode.cpp:442-446) and the hardware-friendly metric update (PM += |LLR|
@@ -96,7 +97,7 @@ int polar_b200_fast_variant_count(void);
 int polar_b200_fast_variant_desc(int index, int* nlog, int* lanes_log2, int* warps_per_block);
 
 /*
- * Test hooks of the list-size-1 first pass of STRICT mode (sc_ssc.cuh: plain SC on the pruned decoding tree, N = 2^8..2^12;
+ * Test hooks of the list-size-1 first pass of the STRICT and FP32 modes (sc_ssc.cuh: plain SC on the pruned decoding tree, N = 2^8..2^12;
  * POLAR_B200_SSC=0 in the environment switches it off, POLAR_B200_INFO_KERNEL_KIND reports 500). No GPU needed.
  * _schedule: the per-code operation list built from frozen_mask ([2^n] bytes); returns its length (0: this code is not
  * served by that kernel), writes it when cap is large enough. _positions: where output bit j is gathered from, [K].

@@ -831,9 +831,9 @@ int decode_any(polar_b200_ctx* c, const Real* llr, int B, int L, uint32_t* info_
     return decode_generic<Real>(c, llr, B, L, info_packed, st);
 }
 
-// plain SC on the pruned tree (sc_ssc.cuh): list size 1 with a flag list, i.e. strict mode's first pass -- the rate-1 node
-// shortcut is exact only while every deciding LLR has a trustworthy sign, which the margin / flag list / second pass
-// take care of. One block per SM; 8 codewords per warp.
+// plain SC on the pruned tree (sc_ssc.cuh): list size 1 with a flag list -- the rate-1 node shortcut is exact only while
+// every deciding LLR has a trustworthy sign, which the margin / flag list / second pass take care of (strict mode: below
+// tau, double; fp32 mode: exact zeros, leaf by leaf in fp32). One block per SM; 8 codewords per warp.
 int decode_ssc(polar_b200_ctx* c, const float* llr, int B, uint32_t* out, cudaStream_t st, float* margin, int* flag_list,
                int* flag_count, float tau, int cw_base, const CountSpec* cs) {
     const ssc::Layout& lay = c->ssc_lay;
@@ -1162,6 +1162,21 @@ int decode_mode(polar_b200_ctx* c, const float* llr, int B, int L, uint32_t* out
     }
     if (margin && fv < 0) return POLAR_B200_E_UNSUPPORTED;       // margins are reported by the fast kernels only
     if (mode == POLAR_B200_MODE_FP32) {
+        if (fv >= 0 && L == 1 && !cs && c->ssc_ok && env_int("POLAR_B200_SSC", 1) != 0 && env_int("POLAR_B200_FAST_VARIANT", -1) < 0) {
+            // list size 1: the pruned-tree kernel (sc_ssc.cuh). Its rate-1 shortcut is not the leaf-by-leaf decoder on a
+            // codeword with an exactly-zero deciding LLR (a tie): those few -- none on a real channel -- are listed by the
+            // kernel (threshold = one step of its fixed point, 6e-8) and decoded leaf by leaf by the generic fp32 kernel.
+            // The list is local to this call (row 0 = llr's first row), so chunks of the host entry point stand alone.
+            int rc = ensure_flags(c, B);
+            if (rc) return rc;
+            CU_TRY(cudaMemsetAsync(c->d_flag_count, 0, sizeof(int), st));
+            rc = decode_fast(c, fv, llr, B, L, out, st, margin, c->d_flag_list, c->d_flag_count, 1.0f / 16777216.0f, 0, nullptr);
+            if (rc) return rc;
+            const int kind = c->last_kernel;
+            rc = decode_generic<float, float>(c, llr, B, L, out, st, c->d_flag_list, c->d_flag_count);
+            c->last_kernel = kind;
+            return rc;
+        }
         if (fv >= 0) return decode_fast(c, fv, llr, B, L, out, st, margin, nullptr, nullptr, 0.0f, 0, cs);
         return count_after(decode_any<float>(c, llr, B, L, out, st));
     }

@@ -1,4 +1,4 @@
-// sc_ssc.cuh -- plain SC (list size 1) as STRICT mode's first pass, N = 2^8 .. 2^12: a second mapping of the same
+// sc_ssc.cuh -- plain SC (list size 1), the first pass of STRICT mode and FP32 mode, N = 2^8 .. 2^12: a second mapping of the same
 // decoder (the reference's decode_scl_llr with list size 1, PolarC/PolarCode.cpp:130-190, 422-473, 489-553) that keeps
 // every byte of a codeword's state on the SM.
 //
@@ -24,7 +24,8 @@
 //     holds in any arithmetic that gets the signs right and breaks only where an entry is zero or so small that its
 //     sign is in doubt -- which is what STRICT mode's margin is for: the smallest |LLR| over every entry that decided a
 //     bit is the codeword's margin, and a codeword below tau is decoded again by the double-precision second pass,
-//     leaf by leaf. This kernel is therefore used in STRICT mode only; FP32 mode keeps the leaf-by-leaf kernel.
+//     leaf by leaf. (FP32 mode, which has no second pass, lists the codewords with an exactly-zero deciding LLR -- ties,
+//     none on a real channel -- the same way and hands them to the leaf-by-leaf generic fp32 kernel.)
 //     At N = 2048, K = 1024: 6 370 check nodes instead of 11 264 (+ 1 024 for the layer-1 entries that are computed
 //     twice), 328 visited nodes instead of 4 095.
 //   * The walk over the tree is a per-code SCHEDULE built once on the host (build_schedule): a few hundred 32-bit

@@ -670,13 +670,17 @@ def test_pruned_tree_sc_kernel(torch_cuda, monkeypatch, n, K, crc, B, eb):
     assert (m >= 0).all() and np.isfinite(m).all()
     assert int((np.round(m * 2 ** 24) < int(np.float32(1e-5) * 2.0 ** 24)).sum()) == flagged      # the kernel's fixed-point threshold
     assert np.array_equal(pc.decode_batch(llr, 1), want)                       # host entry point (chunked)
+    # fp32 mode: the same kernel without the second pass (stated tolerance as for the other fp32 kernels: one codeword)
+    f32 = unpack_bits(pc.decode_device(d_llr, 1, mode="fp32").cpu().numpy().view(np.uint32), K)
+    assert pc.info(6) == 500 and int((f32 != want).any(1).sum()) <= 1
+    assert int((pc.decode_batch(llr, 1, mode="fp32") != want).any(1).sum()) <= 1
     monkeypatch.setenv("POLAR_B200_SSC", "0")
     old = pc.decode_device(d_llr, 1, mode="strict")
     assert 1 <= pc.info(6) < 500
     assert torch.equal(old, out)
 
 
-def test_pruned_tree_sc_kernel_on_ties_and_extremes(torch_cuda):
+def test_pruned_tree_sc_kernel_on_ties_and_extremes(torch_cuda, monkeypatch):
     """Zero, tied, huge and lattice LLRs: the rate-1 shortcut is not valid on a zero entry -- the margin is then 0 and
     strict mode's second pass decodes the codeword leaf by leaf; the result must be the reference's."""
     from polar_b200 import PolarCode
@@ -692,6 +696,17 @@ def test_pruned_tree_sc_kernel_on_ties_and_extremes(torch_cuda):
         got = pc.decode_batch(llr, 1)
         assert pc.info(6) == 500 and pc.last_flagged >= 3
         assert np.array_equal(got, want)
+        # fp32 mode: codewords with a tie are handed to the leaf-by-leaf fp32 kernel, i.e. every row here comes out as the
+        # generic fp32 kernel alone decodes it (which equals the reference on the rows without rounding-sensitive
+        # cancellations: all-zero and constant LLRs)
+        f32 = pc.decode_batch(llr, 1, mode="fp32")
+        assert pc.info(6) == 500
+        assert np.array_equal(f32[:5], want[:5])
+        monkeypatch.setenv("POLAR_B200_FORCE_GENERIC", "1")
+        gen = pc.decode_batch(llr, 1, mode="fp32")
+        assert pc.info(6) == 0
+        monkeypatch.delenv("POLAR_B200_FORCE_GENERIC")
+        assert np.array_equal(f32, gen)
 
 
 MINSUM = [(11, 1024, 16, 32, 128, 1.5), (11, 1024, 0, 1, 2048, 2.0), (11, 1024, 16, 4, 512, 1.5), (9, 256, 0, 32, 512, 2.0),
