@@ -860,10 +860,16 @@ int decode_ssc(polar_b200_ctx* c, const float* llr, int B, uint32_t* out, cudaSt
     a.tauq = a.tauq_flag; a.tau = tau;
     A.sched = c->d_ssc_sched; A.pos = c->d_ssc_pos; A.lay = lay;
     A.sync_rounds = env_int("POLAR_B200_SSC_SYNC", 1);
-    int wpb = env_int("POLAR_B200_SSC_WARPS", lay.warps);
+    // Warps per SM: as many as fit (lay.warps) for the number of rounds that takes, but no more than fills those rounds
+    // evenly -- the kernel is latency-bound, every warp fewer on an SM makes the others faster, and a small batch is
+    // better spread thinly over all SMs than packed onto a few (N = 512, 4 096 codewords: 32 blocks x 16 warps took 83 us).
+    const long long groups = ((long long)B + 7) / 8;
+    const long long rounds = (groups + (long long)c->sm_count * lay.warps - 1) / ((long long)c->sm_count * lay.warps);
+    int wpb = (int)((groups + (long long)c->sm_count * rounds - 1) / ((long long)c->sm_count * rounds));
+    wpb = env_int("POLAR_B200_SSC_WARPS", wpb);
     if (wpb < 1 || wpb > lay.warps) wpb = lay.warps;
     int blocks = c->sm_count;
-    const int need = (B + 8 * wpb - 1) / (8 * wpb);
+    const int need = (int)((groups + wpb - 1) / wpb);
     if (blocks > need) blocks = need;
     kern<<<blocks, wpb * 32, lay.bytes * wpb, st>>>(A);
     CU_TRY(cudaGetLastError());
